@@ -1,0 +1,154 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// Thin extern "C" driver around the UNMODIFIED reference headers (compiled from /root/reference where
+// they lie; nothing is copied).  It is built by oracle/Makefile into oracle/_ref/libnflref.so and is used
+//   * by tests/ to pin the C restatement (oracle/nfl_oracle.c) and the CUDA path bit-for-bit, and
+//   * by bench.py's cpu_baseline / --impl reference leg (kind = "reference").
+// The product (nfllib_b200/) never loads this library.
+//
+// Every operation goes through the reference's own public surface:
+//   fwd        -> nfl::poly::ntt_pow_phi()            include/nfl/poly.hpp:167
+//   inv        -> nfl::poly::invntt_pow_invphi()      include/nfl/poly.hpp:168
+//   mul/add/sub-> operator* / + / -                   include/nfl/poly.hpp:346-350
+//   mul_shoup  -> nfl::shoup(a * b, bprime)           include/nfl/ops.hpp:266-277
+//   compute_shoup -> nfl::compute_shoup(a)            include/nfl/poly.hpp:352
+//   raw_ntt    -> poly::core::ntt via the friend proxy, as tests/ntt_perfs.cpp:122-134 does
+//   polymul    -> fwd(a), fwd(b), a*b, inv            (tests/nfllib_demo_main_op.cpp:31-45 pattern)
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include <nfl.hpp>
+
+namespace nfl { namespace tests {
+// Same friend-proxy trick as tests/ntt_perfs.cpp:122-134 (poly.hpp:71-76 declares the friend).
+template <class P>
+class poly_tests_proxy {
+public:
+  static void raw_ntt(P &p, size_t cm) {
+    P::core::ntt(&p(cm, 0), p.base.omegas[cm], p.base.shoupomegas[cm], P::get_modulus(cm));
+  }
+};
+}}
+
+namespace {
+
+enum Op { OP_FWD = 0, OP_INV, OP_MUL, OP_MUL_SHOUP, OP_COMPUTE_SHOUP, OP_ADD, OP_SUB, OP_RAW_NTT, OP_POLYMUL,
+          OP_MULADD /* out = a + b*c, expression-fused */ };
+
+template <class P>
+void *aligned_polys(size_t n) {
+  void *ptr = nullptr;
+  if (posix_memalign(&ptr, 32, n * sizeof(P)) != 0) return nullptr;
+  return ptr;
+}
+
+// One thread's share: polys [lo, hi).  Buffers are raw [batch][M][N] arrays == arrays of poly (poly.hpp:87-88).
+template <class P>
+void run_range(int op, P *out, const P *a, const P *b, const P *c, size_t lo, size_t hi) {
+  for (size_t i = lo; i < hi; ++i) {
+    switch (op) {
+      case OP_FWD: out[i].ntt_pow_phi(); break;          // run_config already copied a -> out
+      case OP_INV: out[i].invntt_pow_invphi(); break;
+      case OP_MUL: out[i] = a[i] * b[i]; break;
+      case OP_MUL_SHOUP: out[i] = nfl::shoup(a[i] * b[i], c[i]); break;
+      case OP_COMPUTE_SHOUP: out[i] = nfl::compute_shoup(a[i]); break;
+      case OP_ADD: out[i] = a[i] + b[i]; break;
+      case OP_SUB: out[i] = a[i] - b[i]; break;
+      case OP_MULADD: out[i] = a[i] + b[i] * c[i]; break;
+      case OP_RAW_NTT:
+        if (out != a) std::memcpy(&out[i], &a[i], sizeof(P));
+        for (size_t cm = 0; cm < P::nmoduli; ++cm) nfl::tests::poly_tests_proxy<P>::raw_ntt(out[i], cm);
+        break;
+      case OP_POLYMUL: {
+        P *ta = static_cast<P *>(aligned_polys<P>(2));
+        std::memcpy(&ta[0], &a[i], sizeof(P));
+        std::memcpy(&ta[1], &b[i], sizeof(P));
+        ta[0].ntt_pow_phi();
+        ta[1].ntt_pow_phi();
+        out[i] = ta[0] * ta[1];
+        out[i].invntt_pow_invphi();
+        free(ta);
+      } break;
+    }
+  }
+}
+
+template <class P>
+int run_config(int op, void *out, const void *a, const void *b, const void *c, size_t batch, int threads) {
+  P *po = static_cast<P *>(out);
+  const P *pa = static_cast<const P *>(a), *pb = static_cast<const P *>(b), *pc = static_cast<const P *>(c);
+  if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+       reinterpret_cast<uintptr_t>(c)) & 31)
+    return -2;  // reference asserts 32-byte alignment (core.hpp:88)
+  if (op == OP_FWD || op == OP_INV) {
+    if (out != a) std::memcpy(out, a, batch * sizeof(P));
+    pa = po;
+  }
+  if (threads <= 1) {
+    run_range<P>(op, po, pa, pb, pc, 0, batch);
+    return 0;
+  }
+  std::vector<std::thread> pool;
+  size_t per = (batch + threads - 1) / threads;
+  for (int t = 0; t < threads; ++t) {
+    size_t lo = t * per, hi = std::min(batch, lo + per);
+    if (lo >= hi) break;
+    pool.emplace_back(run_range<P>, op, po, pa, pb, pc, lo, hi);
+  }
+  for (auto &th : pool) th.join();
+  return 0;
+}
+
+}  // namespace
+
+#define NFLREF_CONFIG(T, BITS, N, M) \
+  if (limb_bits == BITS && degree == N && nmoduli == M) \
+    return run_config<nfl::poly<T, N, M>>(op, out, a, b, c, batch, threads);
+
+#define NFLREF_CAT2(a, b) a##b
+#define NFLREF_CAT(a, b) NFLREF_CAT2(a, b)
+
+extern "C" {
+
+// The instantiation list is split over several translation units (NFLREF_PART = 0..5) only so that
+// `make -j` can build them in parallel; ref_dispatch.cpp tries each part in turn.
+// Returns 0 on success, -1 if (limb_bits, degree, nmoduli) is not in this part, -2 on misaligned buffers.
+int NFLREF_CAT(nflref_run_part, NFLREF_PART)(int op, int limb_bits, size_t degree, size_t nmoduli, void *out,
+                                             const void *a, const void *b, const void *c, size_t batch,
+                                             int threads) {
+#include "ref_configs.inc"
+  return -1;
+}
+
+#if NFLREF_PART == 0
+
+// Tables of the reference, for pinning our own parameter derivation (include/nfl/params.hpp).
+int nflref_params(int limb_bits, size_t count, uint64_t *P, uint64_t *Pn, uint64_t *roots, uint64_t *invkmax,
+                  uint64_t *kmax, uint64_t *maxmoduli) {
+#define DUMP(T) \
+  { *kmax = nfl::params<T>::kMaxPolyDegree; *maxmoduli = nfl::params<T>::kMaxNbModuli; \
+    for (size_t i = 0; i < count && i < nfl::params<T>::kMaxNbModuli; ++i) { \
+      P[i] = nfl::params<T>::P[i]; Pn[i] = nfl::params<T>::Pn[i]; \
+      roots[i] = nfl::params<T>::primitive_roots[i]; invkmax[i] = nfl::params<T>::invkMaxPolyDegree[i]; } \
+    return 0; }
+  if (limb_bits == 16) DUMP(uint16_t)
+  if (limb_bits == 32) DUMP(uint32_t)
+  if (limb_bits == 64) DUMP(uint64_t)
+  return -1;
+}
+
+const char *nflref_build_flags(void) {
+#if defined(NTT_AVX2)
+  return "NFL_OPTIMIZED NTT_AVX2";
+#elif defined(NTT_SSE)
+  return "NFL_OPTIMIZED NTT_SSE";
+#else
+  return "serial";
+#endif
+}
+
+#endif  // NFLREF_PART == 0
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+"""TEST INFRASTRUCTURE: ctypes bindings for the CPU oracle (oracle/liboracle.so, the C restatement) and,
+when it has been built, the unmodified reference (oracle/_ref/libnflref.so).  Never imported by the product."""
+import ctypes
+import json
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnflref.so")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+DTYPES = {16: np.uint16, 32: np.uint32, 64: np.uint64}
+OPS = {"fwd": 0, "inv": 1, "mul": 2, "mul_shoup": 3, "compute_shoup": 4, "add": 5, "sub": 6, "raw_ntt": 7,
+       "polymul": 8, "muladd": 9}
+
+
+def aligned(shape, dtype, align=64):
+    """numpy array whose data pointer is `align`-byte aligned (reference asserts 32, core.hpp:88)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.zeros(n + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
+def as_aligned(a):
+    if a.ctypes.data % 32 == 0 and a.flags["C_CONTIGUOUS"]:
+        return a
+    b = aligned(a.shape, a.dtype)
+    b[...] = a
+    return b
+
+
+_params_cache = {}
+
+
+def golden_params(bits):
+    """First entries of params<T>::{P,Pn,primitive_roots,invkMaxPolyDegree} (tests/golden/params.json)."""
+    if not _params_cache:
+        with open(os.path.join(GOLDEN, "params.json")) as f:
+            _params_cache.update({int(k): v for k, v in json.load(f).items()})
+    return _params_cache[bits]
+
+
+class Oracle:
+    """C restatement of the reference path (oracle/nfl_oracle.c)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = ctypes.CDLL(ORACLE_SO)
+            L.nflo_create.restype = ctypes.c_void_p
+            L.nflo_create.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t] + [ctypes.c_void_p] * 4 + [ctypes.c_uint64]
+            L.nflo_destroy.argtypes = [ctypes.c_void_p]
+            L.nflo_run.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_size_t]
+            L.nflo_spec_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, bits, N, M, params=None):
+        g = params or golden_params(bits)
+        self.bits, self.N, self.M = bits, N, M
+        self.dtype = DTYPES[bits]
+        mk = lambda k: np.array(g[k][:M], dtype=np.uint64)
+        self.P, self.Pn, self.roots, self.invk = mk("P"), mk("Pn"), mk("roots"), mk("invkmax")
+        assert len(self.P) == M, "not enough golden moduli"
+        self.h = self.lib().nflo_create(bits, N, M, self.P.ctypes.data, self.Pn.ctypes.data, self.roots.ctypes.data,
+                                        self.invk.ctypes.data, g["kmax"])
+        assert self.h, "nflo_create failed"
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib().nflo_destroy(self.h)
+            self.h = None
+
+    def run(self, op, a, b=None, c=None):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        out = np.empty_like(a)
+        ptr = lambda x: None if x is None else np.ascontiguousarray(x, dtype=self.dtype).ctypes.data
+        keep = [np.ascontiguousarray(x, dtype=self.dtype) for x in (b, c) if x is not None]
+        pb = keep[0].ctypes.data if b is not None else None
+        pc = keep[-1].ctypes.data if c is not None else None
+        rc = self.lib().nflo_run(self.h, OPS[op], out.ctypes.data, a.ctypes.data, pb, pc, a.size // (self.N * self.M))
+        assert rc == 0
+        return out
+
+    def spec_fwd(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        out = np.empty_like(a)
+        self.lib().nflo_spec_fwd(self.h, out.ctypes.data, a.ctypes.data, a.size // (self.N * self.M))
+        return out
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class Ref:
+    """The unmodified reference compiled into oracle/_ref/libnflref.so (oracle/ref_harness.cpp)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            L = ctypes.CDLL(REF_SO)
+            L.nflref_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t] + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_int]
+            L.nflref_build_flags.restype = ctypes.c_char_p
+            cls._lib = L
+        return cls._lib
+
+    def __init__(self, bits, N, M):
+        self.bits, self.N, self.M, self.dtype = bits, N, M, DTYPES[bits]
+
+    def supported(self):
+        z = aligned((1, self.M, self.N), self.dtype)
+        return self.lib().nflref_run(OPS["add"], self.bits, self.N, self.M, z.ctypes.data, z.ctypes.data, z.ctypes.data, None, 0, 1) == 0
+
+    def run(self, op, a, b=None, c=None, threads=1, out=None):
+        a = as_aligned(np.ascontiguousarray(a, dtype=self.dtype))
+        b = None if b is None else as_aligned(np.ascontiguousarray(b, dtype=self.dtype))
+        c = None if c is None else as_aligned(np.ascontiguousarray(c, dtype=self.dtype))
+        if out is None:
+            out = aligned(a.shape, self.dtype)
+        rc = self.lib().nflref_run(OPS[op], self.bits, self.N, self.M, out.ctypes.data, a.ctypes.data,
+                                   None if b is None else b.ctypes.data, None if c is None else c.ctypes.data,
+                                   a.size // (self.N * self.M), threads)
+        assert rc == 0, f"nflref_run rc={rc} for ({self.bits},{self.N},{self.M})"
+        return out
+
+    @classmethod
+    def params(cls, bits, count):
+        L = cls.lib()
+        arrs = [np.zeros(count, np.uint64) for _ in range(4)]
+        k, mm = ctypes.c_uint64(), ctypes.c_uint64()
+        L.nflref_params(bits, ctypes.c_size_t(count), *[x.ctypes.data_as(ctypes.c_void_p) for x in arrs], ctypes.byref(k), ctypes.byref(mm))
+        n = min(count, mm.value)
+        return {"P": [int(v) for v in arrs[0][:n]], "Pn": [int(v) for v in arrs[1][:n]], "roots": [int(v) for v in arrs[2][:n]],
+                "invkmax": [int(v) for v in arrs[3][:n]], "kmax": k.value, "maxmoduli": mm.value}
+
+
+def splitmix64(seed, n):
+    """Deterministic uint64 stream (splitmix64), vectorised."""
+    idx = np.arange(1, n + 1, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return z
+
+
+def random_polys(bits, N, M, batch, seed, P=None):
+    """[batch][M][N] coefficients i.i.d. uniform in [0, p_cm)."""
+    P = P if P is not None else golden_params(bits)["P"]
+    r = splitmix64(seed, batch * M * N).reshape(batch, M, N)
+    out = np.empty((batch, M, N), dtype=DTYPES[bits])
+    for cm in range(M):
+        out[:, cm, :] = (r[:, cm, :] % np.uint64(P[cm])).astype(DTYPES[bits])
+    return out

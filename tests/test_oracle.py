@@ -1,0 +1,116 @@
+"""Pins the CPU oracle (oracle/nfl_oracle.c):
+  * against committed fixtures that were produced by the unmodified reference (tests/golden/gen_golden.py),
+  * against the closed-form definition out[j] = a(phi^(2*bitrev(j)+1)),
+  * and, when oracle/_ref/libnflref.so is present, bit-for-bit against the reference itself on every size.
+Mirrors the reference's own checks: tests/nfl_{add,sub,mul}.cpp (op vs naive formula), tests/poly_p.cpp:52-58
+(NTT round trip) -- but always with full-array equality, never the reference's any-equal operator==."""
+import glob
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle_lib import GOLDEN, DTYPES, Oracle, Ref, have_ref, golden_params, random_polys
+
+KATS = sorted(glob.glob(os.path.join(GOLDEN, "kat_*.npz")))
+
+
+def _cfg(path):
+    m = re.search(r"kat_u(\d+)_n(\d+)_m(\d+)", path)
+    return tuple(int(x) for x in m.groups())
+
+
+@pytest.mark.parametrize("path", KATS, ids=[os.path.basename(p) for p in KATS])
+def test_oracle_matches_reference_fixtures(path):
+    bits, N, M = _cfg(path)
+    k = np.load(path)
+    o = Oracle(bits, N, M)
+    a, b = k["a"], k["b"]
+    assert np.array_equal(o.run("fwd", a), k["fwd_a"])
+    assert np.array_equal(o.run("fwd", b), k["fwd_b"])
+    assert np.array_equal(o.run("inv", a), k["inv_a"])
+    assert np.array_equal(o.run("raw_ntt", a), k["raw_ntt"])
+    assert np.array_equal(o.run("mul", a, b), k["mul"])
+    assert np.array_equal(o.run("add", a, b), k["add"])
+    assert np.array_equal(o.run("sub", a, b), k["sub"])
+    assert np.array_equal(o.run("compute_shoup", b), k["shoup_b"])
+    assert np.array_equal(o.run("mul_shoup", a, b, k["shoup_b"]), k["mul_shoup"])
+    assert np.array_equal(o.run("polymul", a, b), k["polymul"])
+    assert np.array_equal(o.run("muladd", a, b, k["fwd_a"]), k["muladd"])
+    # round trip (tests/poly_p.cpp:52-58 pattern, but a strong comparison)
+    assert np.array_equal(o.run("inv", k["fwd_a"]), a)
+
+
+@pytest.mark.parametrize("bits,N,M", [(64, 2, 1), (64, 4, 1), (64, 8, 2), (64, 64, 2), (32, 8, 2), (32, 128, 3), (16, 16, 1), (16, 64, 2)])
+def test_oracle_matches_closed_form(bits, N, M):
+    if N == 2:
+        pytest.skip("reference's degree==2 path returns lazily reduced values (core.hpp:468-483)")
+    o = Oracle(bits, N, M)
+    a = random_polys(bits, N, M, 3, 42 + N)
+    assert np.array_equal(o.run("fwd", a), o.spec_fwd(a))
+
+
+def test_oracle_negacyclic_shift():
+    """inv(fwd(a) * fwd(X)) = X*a mod (X^N + 1): coefficients shift up by one, the wrapped one is negated."""
+    bits, N, M = 64, 256, 2
+    o = Oracle(bits, N, M)
+    a = random_polys(bits, N, M, 2, 5)
+    x = np.zeros_like(a)
+    x[:, :, 1] = 1
+    got = o.run("polymul", a, x)
+    P = golden_params(bits)["P"]
+    exp = np.roll(a, 1, axis=2)
+    for cm in range(M):
+        exp[:, cm, 0] = (np.uint64(P[cm]) - a[:, cm, N - 1]) % np.uint64(P[cm])
+    assert np.array_equal(got, exp)
+
+
+def test_oracle_hashes_at_baseline_configs():
+    """sha256 of reference outputs on seeded inputs at the BASELINE.json shapes (tests/golden/hashes.json)."""
+    with open(os.path.join(GOLDEN, "hashes.json")) as f:
+        hs = json.load(f)
+    h = lambda x: hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()
+    for name, e in hs.items():
+        if e["N"] * e["M"] * e["batch"] > 1 << 17:
+            continue  # keep the CPU suite quick; the GPU parity tests cover every entry
+        o = Oracle(e["bits"], e["N"], e["M"])
+        a = random_polys(e["bits"], e["N"], e["M"], e["batch"], e["seed_a"])
+        b = random_polys(e["bits"], e["N"], e["M"], e["batch"], e["seed_b"])
+        assert h(a) == e["in_a"]
+        assert h(o.run("fwd", a)) == e["fwd_a"], name
+        assert h(o.run("mul", a, b)) == e["mul"], name
+        assert h(o.run("polymul", a, b)) == e["polymul"], name
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("bits", [16, 32, 64])
+def test_oracle_matches_live_reference_all_sizes(bits):
+    lo = {16: 4, 32: 3, 64: 2}[bits]  # sizeof(poly) is padded to 32 B below these (poly.hpp:88)
+    hi = {16: 9, 32: 15, 64: 15}[bits]
+    for ln in range(lo, hi + 1):
+        N = 1 << ln
+        r = Ref(bits, N, 1)
+        if not r.supported():
+            continue
+        o = Oracle(bits, N, 1)
+        batch = 2 if N >= 8192 else 4
+        a = random_polys(bits, N, 1, batch, 100 + ln)
+        b = random_polys(bits, N, 1, batch, 200 + ln)
+        for op in ("fwd", "inv", "raw_ntt"):
+            assert np.array_equal(o.run(op, a), r.run(op, a)), (bits, N, op)
+        for op in ("mul", "add", "sub"):
+            assert np.array_equal(o.run(op, a, b), r.run(op, a, b)), (bits, N, op)
+        bs = r.run("compute_shoup", b)
+        assert np.array_equal(o.run("compute_shoup", b), bs)
+        assert np.array_equal(o.run("mul_shoup", a, b, bs), r.run("mul_shoup", a, b, bs))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so not built (needs /root/reference)")
+def test_golden_params_match_live_reference():
+    for bits in (16, 32, 64):
+        g = golden_params(bits)
+        live = Ref.params(bits, 16)
+        assert g == live
