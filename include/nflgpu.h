@@ -1,0 +1,135 @@
+/*
+ * nflgpu.h — C ABI of the B200-native NTT / pointwise hot path of NFLlib.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer: its hot path sits
+ * behind the compile-time template surface nfl::poly<T,Degree,NbModuli> (include/nfl/poly.hpp:82-309) whose
+ * backend seam is the CC_SIMD tag (include/nfl/arch.hpp:6-18).  The C++11 header include/nfl_b200.hpp keeps
+ * that template surface and forwards to the entry points below; each entry point names the reference
+ * function it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns 0 on success or a negative nflgpu_status; nflgpu_last_error() returns a
+ *     thread-local message for the last failure on the calling thread; nothing throws across the ABI;
+ *   - a "batch buffer" is `batch` polynomials laid out exactly like an array of nfl::poly
+ *     (poly.hpp:87-88,156-157):  limb[batch][nmoduli][degree], residue-major, little-endian limbs of
+ *     `limb_bits` bits; device buffers must be 16-byte aligned;
+ *   - coefficients must be canonical, i.e. < p_cm (the reference's contract, ops.hpp:131,148,190); outputs
+ *     are canonical and bit-identical to the reference's;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls on one stream are
+ *     ordered; a context is bound to one device; distinct contexts are independent;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point fails with
+ *     NFLGPU_ERR_CUDA.
+ */
+#ifndef NFLGPU_H
+#define NFLGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nflgpu_ctx nflgpu_ctx;
+
+typedef enum {
+  NFLGPU_OK = 0,
+  NFLGPU_ERR_ARG = -1,         /* bad argument (size, alignment, null pointer) */
+  NFLGPU_ERR_UNSUPPORTED = -2, /* (limb_bits, degree, nmoduli) outside what the kernels are built for */
+  NFLGPU_ERR_CUDA = -3,        /* CUDA runtime / driver error, or no device */
+  NFLGPU_ERR_ALLOC = -4        /* host or device allocation failed */
+} nflgpu_status;
+
+/* ---- context ------------------------------------------------------------------------------------------ */
+
+/* Creates the per-(limb, degree, nmoduli) state that nfl::poly<T,Degree,NbModuli>::core::initialize()
+ * builds at static-init time (core.hpp:625-686): moduli, the psi / psi^-1 twiddle tables with their Shoup
+ * companions, N^-1.  Tables are derived from the moduli and the primitive 2*kMaxPolyDegree-th roots exactly
+ * as core.hpp:640-665 derives phi and N^-1, then uploaded to `device`.
+ *   limb_bits      16, 32 or 64  (params<uint16_t|uint32_t|uint64_t>, params.hpp:12,44,83)
+ *   degree         power of two, 32 bytes <= degree*limb_bits/8, degree <= 32768 (16384 for 64-bit limbs)
+ *   first_modulus  index of the first modulus in NFLlib's table; a context covers
+ *                  P[first_modulus .. first_modulus+nmoduli) — nonzero when residues are sharded over GPUs
+ *   moduli, roots  optional caller-provided tables of `nmoduli` uint64_t each (params<T>::P and
+ *                  params<T>::primitive_roots, widened); pass NULL for both to use the built-in derivation
+ *                  of NFLlib's tables (nflgpu_params_*). */
+int nflgpu_ctx_create(nflgpu_ctx **ctx, int limb_bits, size_t degree, size_t nmoduli, size_t first_modulus,
+                      int device, const uint64_t *moduli, const uint64_t *roots);
+int nflgpu_ctx_destroy(nflgpu_ctx *ctx);
+
+const char *nflgpu_last_error(void);
+
+/* Introspection. */
+int nflgpu_ctx_info(const nflgpu_ctx *ctx, int *limb_bits, size_t *degree, size_t *nmoduli, int *device);
+/* Copies the context's moduli (uint64_t[nmoduli]) — nfl::poly::get_modulus(n), poly.hpp:163. */
+int nflgpu_ctx_moduli(const nflgpu_ctx *ctx, uint64_t *out);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t nflgpu_ctx_launch_count(const nflgpu_ctx *ctx);
+
+/* ---- NFLlib parameter tables (params.hpp:12-119; lib/params/params.cpp) -------------------------------- *
+ * Re-derived, not copied: P[i] are the primes 2^(w-2) - k*2*kMax + 1 in descending order, Pn[i] =
+ * floor(2^(2w)/P[i]) - 2^(w+2), roots[i] = g^((P[i]-1)/(2*kMax)) for the least primitive root g of P[i],
+ * invkmax[i] = kMax^-1 mod P[i].  Any output pointer may be NULL.  `first + count` must not exceed
+ * params<T>::kMaxNbModuli (2 / 291 / 1000). */
+int nflgpu_params(int limb_bits, size_t first, size_t count, uint64_t *P, uint64_t *Pn, uint64_t *roots,
+                  uint64_t *invkmax);
+int nflgpu_params_limits(int limb_bits, uint64_t *kMaxPolyDegree, uint64_t *kMaxNbModuli,
+                         unsigned *kModulusBitsize);
+
+/* ---- device batch buffers ------------------------------------------------------------------------------ */
+
+size_t nflgpu_batch_bytes(const nflgpu_ctx *ctx, size_t batch);
+int nflgpu_alloc(nflgpu_ctx *ctx, size_t batch, void **dptr);
+int nflgpu_free(nflgpu_ctx *ctx, void *dptr);
+int nflgpu_upload(nflgpu_ctx *ctx, void *dst_dev, const void *src_host, size_t batch, void *stream);
+int nflgpu_download(nflgpu_ctx *ctx, void *dst_host, const void *src_dev, size_t batch, void *stream);
+int nflgpu_sync(nflgpu_ctx *ctx, void *stream);
+
+/* ---- transforms on device-resident batches -------------------------------------------------------------- */
+
+/* nfl::poly::ntt_pow_phi() (poly.hpp:167 -> core.hpp:594-600 -> core.hpp:455-532 + algos.hpp:16-73):
+ * dst[b][cm][j] = sum_i src[b][cm][i] * phi_cm^(i*(2*bitrev(j)+1)) mod p_cm, canonical.  dst may equal src. */
+int nflgpu_ntt_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream);
+/* nfl::poly::invntt_pow_invphi() (poly.hpp:168 -> core.hpp:608-614, 539-557, permut.hpp): exact inverse of
+ * nflgpu_ntt_fwd (bit-reversed input order, natural output order, canonical).  dst may equal src. */
+int nflgpu_ntt_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream);
+
+/* ---- pointwise functors (the expression evaluator core.hpp:24-37 applied to one functor) ---------------- */
+
+/* operator*  = ops::mulmod        (ops.hpp:184-219) */
+int nflgpu_mul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream);
+/* operator+  = ops::addmod        (ops.hpp:124-135) */
+int nflgpu_add(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream);
+/* operator-  = ops::submod        (ops.hpp:141-151) */
+int nflgpu_sub(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream);
+/* shoup(a*b, bprime) = ops::mulmod_shoup (ops.hpp:225-242, rewrite rule ops.hpp:266-277) */
+int nflgpu_mul_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *bprime,
+                     size_t batch, void *stream);
+/* compute_shoup(a) = ops::compute_shoup (ops.hpp:165-177): floor((a mod p) * 2^w / p) */
+int nflgpu_compute_shoup(nflgpu_ctx *ctx, void *dst, const void *a, size_t batch, void *stream);
+/* a + b*c in one pass = the fused expression `a + b*c` (tests/nfllib_demo_main_op.cpp:232-258);
+ * same values as ops::muladd (opt/ops.hpp:9-48). */
+int nflgpu_muladd(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *c, size_t batch,
+                  void *stream);
+/* a + shoup(b*c, cprime) = ops::muladd_shoup (opt/ops.hpp:56-78), canonical result. */
+int nflgpu_muladd_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *c,
+                        const void *cprime, size_t batch, void *stream);
+
+/* ---- fused negacyclic product ---------------------------------------------------------------------------- */
+
+/* dst = invntt_pow_invphi( ntt_pow_phi(a) * ntt_pow_phi(b) )  — the four reference calls of
+ * tests/nfllib_demo_main_op.cpp:31-45 — i.e. a*b mod (X^N + 1, p_cm), coefficient domain in and out. */
+int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream);
+
+/* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
+ * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked
+ * and double-buffered over two streams.  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,
+ * 6 sub, 8 polymul, 9 muladd.  Unused operands are NULL.  These are the calls bench.py's e2e figure times. */
+int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host,
+                   const void *c_host, size_t batch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFLGPU_H */

@@ -1,0 +1,197 @@
+"""ctypes binding of include/nflgpu.h (one-to-one; see the header for the reference function each entry point
+replaces).  Device buffers are raw device pointers (ints), e.g. torch tensors' .data_ptr()."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DTYPES = {16: np.uint16, 32: np.uint32, 64: np.uint64}
+HOST_OPS = {"fwd": 0, "inv": 1, "mul": 2, "mul_shoup": 3, "compute_shoup": 4, "add": 5, "sub": 6, "polymul": 8, "muladd": 9}
+
+
+class NflGpuError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libnflgpu.so")
+
+
+_lib = None
+
+
+def lib():
+    """Loads libnflgpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise NflGpuError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C nfllib_b200/csrc). There is no CPU fallback.")
+        L = ctypes.CDLL(path)
+        vp, sz, u64p, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int
+        L.nflgpu_last_error.restype = ctypes.c_char_p
+        L.nflgpu_ctx_create.argtypes = [ctypes.POINTER(vp), ci, sz, sz, sz, ci, vp, vp]
+        L.nflgpu_ctx_destroy.argtypes = [vp]
+        L.nflgpu_ctx_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(sz), ctypes.POINTER(sz), ctypes.POINTER(ci)]
+        L.nflgpu_ctx_moduli.argtypes = [vp, vp]
+        L.nflgpu_ctx_launch_count.argtypes = [vp]
+        L.nflgpu_ctx_launch_count.restype = ctypes.c_uint64
+        L.nflgpu_params.argtypes = [ci, sz, sz, vp, vp, vp, vp]
+        L.nflgpu_params_limits.argtypes = [ci, u64p, u64p, ctypes.POINTER(ctypes.c_uint)]
+        L.nflgpu_batch_bytes.argtypes = [vp, sz]
+        L.nflgpu_batch_bytes.restype = sz
+        L.nflgpu_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+        L.nflgpu_free.argtypes = [vp, vp]
+        L.nflgpu_upload.argtypes = [vp, vp, vp, sz, vp]
+        L.nflgpu_download.argtypes = [vp, vp, vp, sz, vp]
+        L.nflgpu_sync.argtypes = [vp, vp]
+        for name in ("nflgpu_ntt_fwd", "nflgpu_ntt_inv", "nflgpu_compute_shoup"):
+            getattr(L, name).argtypes = [vp, vp, vp, sz, vp]
+        for name in ("nflgpu_mul", "nflgpu_add", "nflgpu_sub", "nflgpu_polymul"):
+            getattr(L, name).argtypes = [vp, vp, vp, vp, sz, vp]
+        for name in ("nflgpu_mul_shoup", "nflgpu_muladd"):
+            getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp]
+        L.nflgpu_muladd_shoup.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nflgpu_host_op.argtypes = [vp, ci, vp, vp, vp, vp, sz]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise NflGpuError(f"nflgpu error {rc}: {lib().nflgpu_last_error().decode()}")
+
+
+def params_limits(bits):
+    k, m, b = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint()
+    _check(lib().nflgpu_params_limits(bits, ctypes.byref(k), ctypes.byref(m), ctypes.byref(b)))
+    return {"kmax": k.value, "maxmoduli": m.value, "modulus_bits": b.value}
+
+
+def params(bits, first, count):
+    arrs = [np.zeros(count, np.uint64) for _ in range(4)]
+    _check(lib().nflgpu_params(bits, first, count, *[a.ctypes.data for a in arrs]))
+    return dict(zip(("P", "Pn", "roots", "invkmax"), arrs))
+
+
+class Context:
+    """nflgpu_ctx: the per-(limb, degree, nmoduli) state of nfl::poly<T,Degree,NbModuli>::core on one device."""
+
+    def __init__(self, bits, degree, nmoduli, device=0, first_modulus=0, moduli=None, roots=None):
+        self.bits, self.degree, self.nmoduli, self.device = bits, degree, nmoduli, device
+        self.dtype = DTYPES[bits]
+        h = ctypes.c_void_p()
+        keep = None
+        pm = pr = None
+        if moduli is not None:
+            keep = (np.ascontiguousarray(moduli, dtype=np.uint64), np.ascontiguousarray(roots, dtype=np.uint64))
+            pm, pr = keep[0].ctypes.data, keep[1].ctypes.data
+        _check(lib().nflgpu_ctx_create(ctypes.byref(h), bits, degree, nmoduli, first_modulus, device, pm, pr))
+        self.h = h
+        m = np.zeros(nmoduli, np.uint64)
+        _check(lib().nflgpu_ctx_moduli(self.h, m.ctypes.data))
+        self.moduli = m
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nflgpu_ctx_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def batch_bytes(self, batch):
+        return lib().nflgpu_batch_bytes(self.h, batch)
+
+    @property
+    def launch_count(self):
+        return lib().nflgpu_ctx_launch_count(self.h)
+
+    # ---- raw device-pointer calls (stream = cudaStream_t handle as int, 0 = default stream) ----
+    def alloc(self, batch):
+        p = ctypes.c_void_p()
+        _check(lib().nflgpu_alloc(self.h, batch, ctypes.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        _check(lib().nflgpu_free(self.h, dptr))
+
+    def upload(self, dptr, host, batch, stream=0):
+        _check(lib().nflgpu_upload(self.h, dptr, host.ctypes.data, batch, stream))
+
+    def download(self, host, dptr, batch, stream=0):
+        _check(lib().nflgpu_download(self.h, host.ctypes.data, dptr, batch, stream))
+
+    def sync(self, stream=0):
+        _check(lib().nflgpu_sync(self.h, stream))
+
+    def ntt_fwd(self, dst, src, batch, stream=0):
+        _check(lib().nflgpu_ntt_fwd(self.h, dst, src, batch, stream))
+
+    def ntt_inv(self, dst, src, batch, stream=0):
+        _check(lib().nflgpu_ntt_inv(self.h, dst, src, batch, stream))
+
+    def mul(self, dst, a, b, batch, stream=0):
+        _check(lib().nflgpu_mul(self.h, dst, a, b, batch, stream))
+
+    def add(self, dst, a, b, batch, stream=0):
+        _check(lib().nflgpu_add(self.h, dst, a, b, batch, stream))
+
+    def sub(self, dst, a, b, batch, stream=0):
+        _check(lib().nflgpu_sub(self.h, dst, a, b, batch, stream))
+
+    def mul_shoup(self, dst, a, b, bprime, batch, stream=0):
+        _check(lib().nflgpu_mul_shoup(self.h, dst, a, b, bprime, batch, stream))
+
+    def compute_shoup(self, dst, a, batch, stream=0):
+        _check(lib().nflgpu_compute_shoup(self.h, dst, a, batch, stream))
+
+    def muladd(self, dst, a, b, c, batch, stream=0):
+        _check(lib().nflgpu_muladd(self.h, dst, a, b, c, batch, stream))
+
+    def muladd_shoup(self, dst, a, b, c, cprime, batch, stream=0):
+        _check(lib().nflgpu_muladd_shoup(self.h, dst, a, b, c, cprime, batch, stream))
+
+    def polymul(self, dst, a, b, batch, stream=0):
+        _check(lib().nflgpu_polymul(self.h, dst, a, b, batch, stream))
+
+    # ---- host-buffer call (numpy in, numpy out): H2D + kernel(s) + D2H inside the library ----
+    def host_op(self, op, a, b=None, c=None, out=None):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        batch = a.size // (self.degree * self.nmoduli)
+        if out is None:
+            out = np.empty_like(a)
+        ops = [None if x is None else np.ascontiguousarray(x, dtype=self.dtype) for x in (b, c)]
+        _check(lib().nflgpu_host_op(self.h, HOST_OPS[op], out.ctypes.data, a.ctypes.data,
+                                    None if ops[0] is None else ops[0].ctypes.data,
+                                    None if ops[1] is None else ops[1].ctypes.data, batch))
+        return out
+
+    # ---- convenience for tests: run a device-resident op on numpy data through alloc/upload/.../download ----
+    def run_device(self, op, a, b=None, c=None, d=None, inplace=False):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        batch = a.size // (self.degree * self.nmoduli)
+        bufs = []
+        try:
+            for x in (a, b, c, d):
+                if x is None:
+                    bufs.append(None)
+                    continue
+                x = np.ascontiguousarray(x, dtype=self.dtype)
+                p = self.alloc(batch)
+                self.upload(p, x, batch)
+                bufs.append(p)
+            out = bufs[0] if inplace else self.alloc(batch)
+            args = [out] + [p for p in bufs if p is not None]
+            getattr(self, op)(*args, batch)
+            host = np.empty_like(a)
+            self.download(host, out, batch)
+            self.sync()
+            if not inplace:
+                self.free(out)
+            return host
+        finally:
+            for p in bufs:
+                if p is not None:
+                    self.free(p)

@@ -1,0 +1,456 @@
+// C ABI of libnflgpu.so (include/nflgpu.h): context, device buffers, launch wrappers, host-buffer pipeline.
+// No CPU fallback anywhere: every compute entry point ends in a kernel launch or fails.
+#include "../../include/nflgpu.h"
+#include "host_common.hpp"
+#include "ntt_dispatch.h"
+#include "pointwise.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace nflgpu {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string &msg) { g_last_error = msg; }
+
+cudaError_t launch_ntt(int limb_bits, int log2_degree, bool inverse, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
+  switch (limb_bits) {
+    case 64: return inverse ? launch_ntt_u64_inv(log2_degree, l, device, num_sms, stream) : launch_ntt_u64_fwd(log2_degree, l, device, num_sms, stream);
+    case 32: return inverse ? launch_ntt_u32_inv(log2_degree, l, device, num_sms, stream) : launch_ntt_u32_fwd(log2_degree, l, device, num_sms, stream);
+    case 16: return inverse ? launch_ntt_u16_inv(log2_degree, l, device, num_sms, stream) : launch_ntt_u16_fwd(log2_degree, l, device, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+bool ntt_supported(int limb_bits, int n) {
+  switch (limb_bits) {
+    case 64: return n >= 2 && n <= 14;
+    case 32: return n >= 3 && n <= 15;
+    case 16: return n >= 4 && n <= 9;
+  }
+  return false;
+}
+
+}  // namespace nflgpu
+
+using namespace nflgpu;
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      set_error(std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+      return NFLGPU_ERR_CUDA;                                                                            \
+    }                                                                                                    \
+  } while (0)
+
+struct HostStage {  // one slot of the host-buffer pipeline
+  cudaStream_t stream = nullptr;
+  void *dev[4] = {nullptr, nullptr, nullptr, nullptr};   // a, b, c, out
+  void *pin[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned staging (only used for pageable user buffers)
+  size_t polys = 0;
+};
+
+struct nflgpu_ctx {
+  int limb_bits = 0, log2_degree = 0, device = 0, num_sms = 0;
+  size_t degree = 0, nmoduli = 0, first_modulus = 0;
+  size_t limb_bytes = 0;
+  std::vector<uint64_t> moduli;
+  void *d_moduli_word = nullptr;    // Word[nmoduli] for the NTT kernels
+  uint64_t *d_moduli64 = nullptr;   // uint64_t[nmoduli] for the pointwise kernels
+  uint64_t *d_consts = nullptr;     // Barrett constants, pointwise.h
+  void *d_tw_fwd = nullptr, *d_tw_inv = nullptr;
+  std::atomic<uint64_t> launches{0};
+  HostStage stage[3];
+  size_t stage_polys = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_buf(const nflgpu_ctx *ctx, const void *p, const char *name) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  if (!p) { set_error(std::string("null buffer: ") + name); return NFLGPU_ERR_ARG; }
+  if (reinterpret_cast<uintptr_t>(p) & 15) { set_error(std::string("buffer not 16-byte aligned: ") + name); return NFLGPU_ERR_ARG; }
+  return NFLGPU_OK;
+}
+
+int run_ntt(nflgpu_ctx *ctx, bool inverse, void *dst, const void *src, size_t batch, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, src, "src"))) return rc;
+  if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  NttLaunch l;
+  l.src = src; l.dst = dst; l.tw = inverse ? ctx->d_tw_inv : ctx->d_tw_fwd; l.moduli = ctx->d_moduli_word;
+  l.nmoduli = (uint32_t)ctx->nmoduli; l.batch = (uint32_t)batch;
+  CUDA_TRY(launch_ntt(ctx->limb_bits, ctx->log2_degree, inverse, l, ctx->device, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return NFLGPU_OK;
+}
+
+int run_pw(nflgpu_ctx *ctx, int op, int nin, void *dst, const void *a, const void *b, const void *c, const void *d, size_t batch,
+           void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, a, "a"))) return rc;
+  if (nin >= 2 && (rc = check_buf(ctx, b, "b"))) return rc;
+  if (nin >= 3 && (rc = check_buf(ctx, c, "c"))) return rc;
+  if (nin >= 4 && (rc = check_buf(ctx, d, "d"))) return rc;
+  if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  PwArgs p;
+  p.dst = dst; p.a = a; p.b = b; p.c = c; p.d = d;
+  p.moduli = ctx->d_moduli64; p.consts = ctx->d_consts;
+  p.nmoduli = (uint32_t)ctx->nmoduli; p.degree = (uint32_t)ctx->degree; p.log2_degree = (uint32_t)ctx->log2_degree;
+  p.batch = (uint32_t)batch;
+  CUDA_TRY(launch_pointwise(ctx->limb_bits, op, p, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return NFLGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *nflgpu_last_error(void) { return g_last_error.c_str(); }
+
+int nflgpu_params_limits(int limb_bits, uint64_t *kmax, uint64_t *kmaxmod, unsigned *bits) {
+  LimbLimits lim;
+  if (!limb_limits(limb_bits, &lim)) { set_error("limb_bits must be 16, 32 or 64"); return NFLGPU_ERR_ARG; }
+  if (kmax) *kmax = lim.kMaxPolyDegree;
+  if (kmaxmod) *kmaxmod = lim.kMaxNbModuli;
+  if (bits) *bits = lim.kModulusBitsize;
+  return NFLGPU_OK;
+}
+
+int nflgpu_params(int limb_bits, size_t first, size_t count, uint64_t *P, uint64_t *Pn, uint64_t *roots, uint64_t *invkmax) {
+  LimbLimits lim;
+  if (!limb_limits(limb_bits, &lim)) { set_error("limb_bits must be 16, 32 or 64"); return NFLGPU_ERR_ARG; }
+  if (first + count > lim.kMaxNbModuli) { set_error("modulus index beyond params<T>::kMaxNbModuli"); return NFLGPU_ERR_ARG; }
+  if (!derive_params(limb_bits, first, count, P, Pn, roots, invkmax)) { set_error("parameter derivation failed"); return NFLGPU_ERR_ARG; }
+  return NFLGPU_OK;
+}
+
+int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmoduli, size_t first_modulus, int device,
+                      const uint64_t *moduli, const uint64_t *roots) {
+  if (!out) { set_error("null ctx out-pointer"); return NFLGPU_ERR_ARG; }
+  *out = nullptr;
+  LimbLimits lim;
+  if (!limb_limits(limb_bits, &lim)) { set_error("limb_bits must be 16, 32 or 64"); return NFLGPU_ERR_ARG; }
+  int n = 0;
+  while (((size_t)1 << n) < degree) ++n;
+  if (degree == 0 || ((size_t)1 << n) != degree || degree > lim.kMaxPolyDegree) {
+    set_error("degree must be a power of two <= params<T>::kMaxPolyDegree");  // core.hpp:55-60 static_asserts
+    return NFLGPU_ERR_ARG;
+  }
+  if (nmoduli == 0 || ((moduli == nullptr) != (roots == nullptr))) { set_error("bad moduli/roots arguments"); return NFLGPU_ERR_ARG; }
+  if (!moduli && first_modulus + nmoduli > lim.kMaxNbModuli) {
+    set_error("nmoduli exceeds params<T>::kMaxNbModuli");  // core.hpp:57-58
+    return NFLGPU_ERR_ARG;
+  }
+  if (!ntt_supported(limb_bits, n)) {
+    set_error("unsupported (limb_bits, degree): kernels cover 2^2..2^14 (64-bit), 2^3..2^15 (32-bit), 2^4..2^9 (16-bit)");
+    return NFLGPU_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available (libnflgpu has no CPU fallback)");
+    return NFLGPU_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return NFLGPU_ERR_ARG; }
+
+  nflgpu_ctx *ctx = new (std::nothrow) nflgpu_ctx();
+  if (!ctx) { set_error("out of host memory"); return NFLGPU_ERR_ALLOC; }
+  ctx->limb_bits = limb_bits; ctx->degree = degree; ctx->log2_degree = n; ctx->nmoduli = nmoduli;
+  ctx->first_modulus = first_modulus; ctx->device = device; ctx->limb_bytes = limb_bits / 8;
+  ctx->moduli.resize(nmoduli);
+  std::vector<uint64_t> rts(nmoduli);
+  if (moduli) {
+    for (size_t i = 0; i < nmoduli; ++i) { ctx->moduli[i] = moduli[i]; rts[i] = roots[i]; }
+  } else if (!derive_params(limb_bits, first_modulus, nmoduli, ctx->moduli.data(), nullptr, rts.data(), nullptr)) {
+    delete ctx; set_error("parameter derivation failed"); return NFLGPU_ERR_ARG;
+  }
+  const uint64_t beta4 = limb_bits == 64 ? ((uint64_t)1 << 62) : ((uint64_t)1 << (limb_bits - 2));
+  for (size_t i = 0; i < nmoduli; ++i) {
+    const uint64_t p = ctx->moduli[i];
+    // lazy butterflies need 4p < 2^w; the Barrett constants assume floor(2^w / p) == 4 (params.hpp moduli are
+    // just below 2^(w-2)); the root must have order exactly 2*kMax
+    if (p >= beta4 || p <= beta4 / 5 * 4 || powmod64(rts[i], lim.kMaxPolyDegree, p) != p - 1) {
+      delete ctx; set_error("modulus/root pair is not an NFLlib-style (w-2)-bit NTT prime"); return NFLGPU_ERR_ARG;
+    }
+  }
+
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; set_error("cannot query CUDA device"); return NFLGPU_ERR_CUDA; }
+  ctx->num_sms = prop.multiProcessorCount;
+
+  // tables (tables.cpp), narrowed to the kernel word type: 64-bit limbs -> {u64,u64}; 32/16-bit -> {u32,u32}
+  const int word_bits = limb_bits == 64 ? 64 : 32;
+  const size_t tw_entry = limb_bits == 64 ? 16 : 8;
+  std::vector<unsigned char> hf(nmoduli * degree * tw_entry), hi(nmoduli * degree * tw_entry);
+  std::vector<uint64_t> consts(nmoduli);
+  std::vector<unsigned char> words(nmoduli * (word_bits / 8));
+  for (size_t cm = 0; cm < nmoduli; ++cm) {
+    ResidueTables t;
+    build_residue_tables(limb_bits, word_bits, degree, ctx->moduli[cm], rts[cm], lim.kMaxPolyDegree, &t);
+    for (size_t i = 0; i < degree; ++i) {
+      if (word_bits == 64) {
+        uint64_t *f = reinterpret_cast<uint64_t *>(hf.data()) + (cm * degree + i) * 2;
+        uint64_t *v = reinterpret_cast<uint64_t *>(hi.data()) + (cm * degree + i) * 2;
+        f[0] = t.fwd_w[i]; f[1] = t.fwd_ws[i]; v[0] = t.inv_w[i]; v[1] = t.inv_ws[i];
+      } else {
+        uint32_t *f = reinterpret_cast<uint32_t *>(hf.data()) + (cm * degree + i) * 2;
+        uint32_t *v = reinterpret_cast<uint32_t *>(hi.data()) + (cm * degree + i) * 2;
+        f[0] = (uint32_t)t.fwd_w[i]; f[1] = (uint32_t)t.fwd_ws[i]; v[0] = (uint32_t)t.inv_w[i]; v[1] = (uint32_t)t.inv_ws[i];
+      }
+    }
+    const uint64_t p = ctx->moduli[cm];
+    if (limb_bits == 64) { consts[cm] = newton_pn(64, p); reinterpret_cast<uint64_t *>(words.data())[cm] = p; }
+    else {
+      consts[cm] = limb_bits == 32 ? (uint64_t)((((unsigned __int128)1) << 64) / p) : 0;
+      reinterpret_cast<uint32_t *>(words.data())[cm] = (uint32_t)p;
+    }
+  }
+#define CTX_TRY(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      set_error(std::string(#expr) + ": " + cudaGetErrorName(e_));                            \
+      nflgpu_ctx_destroy(ctx);                                                                \
+      return NFLGPU_ERR_CUDA;                                                                 \
+    }                                                                                         \
+  } while (0)
+  CTX_TRY(cudaMalloc(&ctx->d_tw_fwd, hf.size()));
+  CTX_TRY(cudaMalloc(&ctx->d_tw_inv, hi.size()));
+  CTX_TRY(cudaMalloc(&ctx->d_moduli_word, words.size()));
+  CTX_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->d_moduli64), nmoduli * 8));
+  CTX_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->d_consts), nmoduli * 8));
+  CTX_TRY(cudaMemcpy(ctx->d_tw_fwd, hf.data(), hf.size(), cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMemcpy(ctx->d_tw_inv, hi.data(), hi.size(), cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMemcpy(ctx->d_moduli_word, words.data(), words.size(), cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMemcpy(ctx->d_moduli64, ctx->moduli.data(), nmoduli * 8, cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMemcpy(ctx->d_consts, consts.data(), nmoduli * 8, cudaMemcpyHostToDevice));
+#undef CTX_TRY
+  *out = ctx;
+  return NFLGPU_OK;
+}
+
+int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
+  if (!ctx) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  for (auto &s : ctx->stage) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    for (int i = 0; i < 4; ++i) { if (s.dev[i]) cudaFree(s.dev[i]); if (s.pin[i]) cudaFreeHost(s.pin[i]); }
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
+  delete ctx;
+  return NFLGPU_OK;
+}
+
+int nflgpu_ctx_info(const nflgpu_ctx *ctx, int *limb_bits, size_t *degree, size_t *nmoduli, int *device) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  if (limb_bits) *limb_bits = ctx->limb_bits;
+  if (degree) *degree = ctx->degree;
+  if (nmoduli) *nmoduli = ctx->nmoduli;
+  if (device) *device = ctx->device;
+  return NFLGPU_OK;
+}
+
+int nflgpu_ctx_moduli(const nflgpu_ctx *ctx, uint64_t *out) {
+  if (!ctx || !out) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  std::memcpy(out, ctx->moduli.data(), ctx->nmoduli * 8);
+  return NFLGPU_OK;
+}
+
+uint64_t nflgpu_ctx_launch_count(const nflgpu_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+size_t nflgpu_batch_bytes(const nflgpu_ctx *ctx, size_t batch) { return ctx ? batch * ctx->nmoduli * ctx->degree * ctx->limb_bytes : 0; }
+
+int nflgpu_alloc(nflgpu_ctx *ctx, size_t batch, void **dptr) {
+  if (!ctx || !dptr) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  size_t bytes = nflgpu_batch_bytes(ctx, batch);
+  if (cudaMalloc(dptr, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc failed"); return NFLGPU_ERR_ALLOC; }
+  return NFLGPU_OK;
+}
+
+int nflgpu_free(nflgpu_ctx *ctx, void *dptr) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaFree(dptr));
+  return NFLGPU_OK;
+}
+
+int nflgpu_upload(nflgpu_ctx *ctx, void *dst_dev, const void *src_host, size_t batch, void *stream) {
+  if (!ctx || !dst_dev || !src_host) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(dst_dev, src_host, nflgpu_batch_bytes(ctx, batch), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return NFLGPU_OK;
+}
+
+int nflgpu_download(nflgpu_ctx *ctx, void *dst_host, const void *src_dev, size_t batch, void *stream) {
+  if (!ctx || !dst_host || !src_dev) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaMemcpyAsync(dst_host, src_dev, nflgpu_batch_bytes(ctx, batch), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return NFLGPU_OK;
+}
+
+int nflgpu_sync(nflgpu_ctx *ctx, void *stream) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return NFLGPU_OK;
+}
+
+int nflgpu_ntt_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, false, dst, src, batch, stream); }
+int nflgpu_ntt_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, true, dst, src, batch, stream); }
+
+int nflgpu_mul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
+  return run_pw(ctx, PW_MUL, 2, dst, a, b, nullptr, nullptr, batch, stream);
+}
+int nflgpu_add(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
+  return run_pw(ctx, PW_ADD, 2, dst, a, b, nullptr, nullptr, batch, stream);
+}
+int nflgpu_sub(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
+  return run_pw(ctx, PW_SUB, 2, dst, a, b, nullptr, nullptr, batch, stream);
+}
+int nflgpu_mul_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *bprime, size_t batch, void *stream) {
+  return run_pw(ctx, PW_MUL_SHOUP, 3, dst, a, b, bprime, nullptr, batch, stream);
+}
+int nflgpu_compute_shoup(nflgpu_ctx *ctx, void *dst, const void *a, size_t batch, void *stream) {
+  return run_pw(ctx, PW_COMPUTE_SHOUP, 1, dst, a, nullptr, nullptr, nullptr, batch, stream);
+}
+int nflgpu_muladd(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *c, size_t batch, void *stream) {
+  return run_pw(ctx, PW_MULADD, 3, dst, a, b, c, nullptr, batch, stream);
+}
+int nflgpu_muladd_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *c, const void *cprime, size_t batch,
+                        void *stream) {
+  return run_pw(ctx, PW_MULADD_SHOUP, 4, dst, a, b, c, cprime, batch, stream);
+}
+
+int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, a, "a")) || (rc = check_buf(ctx, b, "b"))) return rc;
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  void *tmp = nullptr;
+  const size_t bytes = nflgpu_batch_bytes(ctx, batch);
+  CUDA_TRY(cudaMallocAsync(&tmp, bytes, s));
+  // fwd(a) -> dst, fwd(b) -> tmp, dst = dst * tmp, dst = inv(dst)
+  if ((rc = run_ntt(ctx, false, dst, a, batch, stream)) || (rc = run_ntt(ctx, false, tmp, b, batch, stream)) ||
+      (rc = run_pw(ctx, PW_MUL, 2, dst, dst, tmp, nullptr, nullptr, batch, stream)) || (rc = run_ntt(ctx, true, dst, dst, batch, stream))) {
+    cudaFreeAsync(tmp, s);
+    return rc;
+  }
+  CUDA_TRY(cudaFreeAsync(tmp, s));
+  return NFLGPU_OK;
+}
+
+// ---- host-buffer pipeline ------------------------------------------------------------------------------------
+
+static bool is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
+int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host, const void *c_host, size_t batch) {
+  if (!ctx || !dst_host || !a_host) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  int nin;
+  switch (op) {
+    case 0: case 1: case 4: nin = 1; break;
+    case 2: case 5: case 6: case 8: nin = 2; break;
+    case 3: case 9: nin = 3; break;
+    default: set_error("unknown op"); return NFLGPU_ERR_ARG;
+  }
+  const void *in[3] = {a_host, b_host, c_host};
+  for (int i = 0; i < nin; ++i) if (!in[i]) { set_error("missing operand"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+
+  const size_t poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
+  // chunk: ~32 MiB per operand, at least one polynomial; three stages in flight (H2D / kernel / D2H overlap)
+  size_t chunk = (32u << 20) / poly_bytes;
+  if (chunk == 0) chunk = 1;
+  if (chunk > batch) chunk = batch;
+  if (ctx->stage_polys < chunk) {
+    for (auto &s : ctx->stage) {
+      if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 4; ++i) {
+        if (s.dev[i]) { CUDA_TRY(cudaFree(s.dev[i])); s.dev[i] = nullptr; }
+        if (s.pin[i]) { CUDA_TRY(cudaFreeHost(s.pin[i])); s.pin[i] = nullptr; }
+        CUDA_TRY(cudaMalloc(&s.dev[i], chunk * poly_bytes));
+      }
+    }
+    ctx->stage_polys = chunk;
+  }
+  bool pinned[4] = {is_pinned(a_host), nin >= 2 && is_pinned(b_host), nin >= 3 && is_pinned(c_host), is_pinned(dst_host)};
+  struct Pending { size_t first, count; bool active; } pend[3] = {{0, 0, false}, {0, 0, false}, {0, 0, false}};
+  int rc = NFLGPU_OK;
+  size_t done = 0;
+  for (int k = 0; done < batch || pend[0].active || pend[1].active || pend[2].active; k = (k + 1) % 3) {
+    HostStage &s = ctx->stage[k];
+    if (pend[k].active) {  // retire the chunk that used this stage three steps ago
+      CUDA_TRY(cudaStreamSynchronize(s.stream));
+      if (!pinned[3]) std::memcpy(static_cast<char *>(dst_host) + pend[k].first * poly_bytes, s.pin[3], pend[k].count * poly_bytes);
+      pend[k].active = false;
+    }
+    if (done >= batch) continue;
+    const size_t cnt = (batch - done < chunk) ? batch - done : chunk;
+    for (int i = 0; i < nin; ++i) {
+      const char *src = static_cast<const char *>(in[i]) + done * poly_bytes;
+      if (!pinned[i]) {
+        if (!s.pin[i]) CUDA_TRY(cudaHostAlloc(&s.pin[i], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
+        std::memcpy(s.pin[i], src, cnt * poly_bytes);
+        src = static_cast<const char *>(s.pin[i]);
+      }
+      CUDA_TRY(cudaMemcpyAsync(s.dev[i], src, cnt * poly_bytes, cudaMemcpyHostToDevice, s.stream));
+    }
+    void *st = s.stream;
+    switch (op) {
+      case 0: rc = nflgpu_ntt_fwd(ctx, s.dev[3], s.dev[0], cnt, st); break;
+      case 1: rc = nflgpu_ntt_inv(ctx, s.dev[3], s.dev[0], cnt, st); break;
+      case 2: rc = nflgpu_mul(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
+      case 3: rc = nflgpu_mul_shoup(ctx, s.dev[3], s.dev[0], s.dev[1], s.dev[2], cnt, st); break;
+      case 4: rc = nflgpu_compute_shoup(ctx, s.dev[3], s.dev[0], cnt, st); break;
+      case 5: rc = nflgpu_add(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
+      case 6: rc = nflgpu_sub(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
+      case 8: rc = nflgpu_polymul(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
+      case 9: rc = nflgpu_muladd(ctx, s.dev[3], s.dev[0], s.dev[1], s.dev[2], cnt, st); break;
+    }
+    if (rc != NFLGPU_OK) break;
+    char *out = static_cast<char *>(dst_host) + done * poly_bytes;
+    if (!pinned[3]) {
+      if (!s.pin[3]) CUDA_TRY(cudaHostAlloc(&s.pin[3], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
+      out = static_cast<char *>(s.pin[3]);
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, s.dev[3], cnt * poly_bytes, cudaMemcpyDeviceToHost, s.stream));
+    pend[k] = {done, cnt, true};
+    done += cnt;
+  }
+  if (rc != NFLGPU_OK) for (auto &s : ctx->stage) if (s.stream) cudaStreamSynchronize(s.stream);
+  return rc;
+}
+
+}  // extern "C"

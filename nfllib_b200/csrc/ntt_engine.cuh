@@ -1,0 +1,385 @@
+// Multi-pass register-radix negacyclic NTT kernels for sm_100a (integer pipes + shared memory; no tensor cores:
+// a butterfly network is not a dense contraction).
+//
+// Replaces, for device-resident batches, the reference's
+//   poly::core::ntt_pow_phi      core.hpp:594-600  (phi twist, ops.hpp:227-242  +  core::ntt, core.hpp:455-532,
+//                                                    ntt_loop / ntt_loop_body algos.hpp:16-73, sse.hpp:162-301,
+//                                                    avx2.hpp:160-302)
+//   poly::core::invntt_pow_invphi core.hpp:608-614  (inv_ntt core.hpp:539-557, permut.hpp:13-117, N^-1 phi^-i twist)
+// with the merged-psi formulation (tables.cpp): forward = Cooley-Tukey butterflies, natural order in, the
+// reference's bit-reversed evaluation order out; inverse = Gentleman-Sande butterflies consuming that order.
+// No twist pass, no bit-reversal pass, no separate correction pass: one read and one write of every
+// coefficient per transform.
+//
+// Work decomposition: one (residue, polynomial) unit = a contiguous slab of N limbs.  A CTA is bound to one
+// residue (its twiddles are staged once into shared memory by a TMA bulk copy when they fit), and holds
+// SLOTS groups of TPU = N/E threads; each group walks over the polynomials of the batch.  Inside a unit each
+// thread keeps E = 2^e coefficients in registers and runs up to e butterfly stages per pass (ntt_plan.h);
+// passes exchange coefficients through a padded shared-memory tile (rows of E words + 16 bytes, so both the
+// row-per-thread and the lane-contiguous access patterns are bank-conflict free).
+#ifndef NFLGPU_NTT_ENGINE_CUH
+#define NFLGPU_NTT_ENGINE_CUH
+
+#include "modarith.cuh"
+#include "ntt_plan.h"
+
+namespace nflgpu {
+
+struct NttArgs {
+  const void *src;
+  void *dst;
+  const void *tw;      // TW[nmoduli][N] for this direction
+  const void *moduli;  // Word[nmoduli]
+  uint32_t nmoduli;
+  uint32_t batch;
+  uint32_t ctas_per_residue;
+};
+
+template <int LB, int LOGN> struct NttCfg {
+  typedef Arith<LB> A;
+  typedef typename A::Word Word;
+  typedef typename A::Store Store;
+  typedef typename A::TW TW;
+  static constexpr int WB = A::WORD_BITS;
+  static constexpr int n = LOGN;
+  static constexpr int N = 1 << n;
+  static constexpr int e = plan_e(n, WB);
+  static constexpr int E = 1 << e;
+  static constexpr int NP = plan_npass(n, WB);
+  static constexpr int TPU = N >> e;  // threads per unit
+  static constexpr int VEC = 16 / (int)sizeof(Word);   // words per 16-byte shared-memory vector
+  static constexpr int PADW = VEC;                      // 16 bytes of padding per row of E words
+  static constexpr int ROW = E + PADW;
+  static constexpr int TILE_WORDS = (NP > 1) ? (N >> e) * ROW : 0;
+  static constexpr int TARGET_THREADS = 256;
+  static constexpr int SLOTS = (TPU >= TARGET_THREADS) ? 1 : TARGET_THREADS / TPU;
+  static constexpr int THREADS = TPU * SLOTS;
+  static constexpr int MIN_BLOCKS = (THREADS <= 256) ? 2 : 1;
+  static constexpr bool TW_SMEM = (size_t)N * sizeof(TW) <= 32768;
+  static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)N * sizeof(TW) : 0;
+  static constexpr size_t SMEM_BYTES = TW_BYTES + 16 /* mbarrier */ + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
+  static __device__ __forceinline__ int pad(int pos) { return pos + (pos >> e) * PADW; }
+};
+
+// ---- small PTX helpers ---------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <class C> __device__ __forceinline__ void unit_sync(int slot, int lane_base) {
+  if (C::TPU >= 64) {
+    if (C::SLOTS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(C::TPU) : "memory");
+  } else if (C::TPU == 32) {
+    __syncwarp();
+  } else {
+    __syncwarp((C::TPU >= 32 ? 0xffffffffu : ((1u << (C::TPU & 31)) - 1u)) << lane_base);
+  }
+}
+
+// ---- butterfly networks on the register window -------------------------------------------------------------
+
+// Forward pass PASS: stages s0 .. s0+r-1, Cooley-Tukey, values lazily kept in [0, 4p).
+// tw points at this pass's entry [0][g]; consecutive e_idx are G entries apart.
+template <class C, int PASS> __device__ __forceinline__ void fwd_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
+                                                                      typename C::Word p, typename C::Word twop) {
+  typedef typename C::A A;
+  typedef typename C::Word Word;
+  constexpr int r = plan_r(C::n, C::WB, PASS), G = 1 << plan_s0(C::n, C::WB, PASS), e = C::e;
+#pragma unroll
+  for (int q = 0; q < r; ++q) {
+    const int bit = e - 1 - q;
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) {
+      if (k & (1 << bit)) continue;
+      const int eidx = (1 << q) - 1 + (k >> (e - q));
+      const typename C::TW t = tw[eidx * G];
+      Word X = x[k];
+      if (!(PASS == 0 && q == 0)) X = csub(X, twop);  // first stage sees canonical input
+      const Word T = A::mul_shoup_lazy(x[k | (1 << bit)], A::tw_w(t), A::tw_ws(t), p);
+      x[k] = X + T;
+      x[k | (1 << bit)] = X - T + twop;
+    }
+  }
+}
+
+// Inverse pass PASS: stages s0+r-1 .. s0 (reverse order), Gentleman-Sande, values lazily kept in [0, 2p);
+// the very last stage (PASS 0, q 0) also multiplies by N^-1 and produces canonical values.
+template <class C, int PASS> __device__ __forceinline__ void inv_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
+                                                                      typename C::Word p, typename C::Word twop,
+                                                                      const typename C::TW ninv) {
+  typedef typename C::A A;
+  typedef typename C::Word Word;
+  constexpr int r = plan_r(C::n, C::WB, PASS), G = 1 << plan_s0(C::n, C::WB, PASS), e = C::e;
+#pragma unroll
+  for (int q = r - 1; q >= 0; --q) {
+    const int bit = e - 1 - q;
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) {
+      if (k & (1 << bit)) continue;
+      const int eidx = (1 << q) - 1 + (k >> (e - q));
+      const typename C::TW t = tw[eidx * G];
+      const Word U = x[k], V = x[k | (1 << bit)];
+      const Word D = A::mul_shoup_lazy(U - V + twop, A::tw_w(t), A::tw_ws(t), p);
+      if (PASS == 0 && q == 0) {
+        x[k] = csub(A::mul_shoup_lazy(U + V, A::tw_w(ninv), A::tw_ws(ninv), p), p);
+        x[k | (1 << bit)] = csub(D, p);
+      } else {
+        x[k] = csub(U + V, twop);
+        x[k | (1 << bit)] = D;
+      }
+    }
+  }
+}
+
+// position of register k of thread `tid` in pass PASS
+template <class C, int PASS> __device__ __forceinline__ int pass_pos(int tid, int k) {
+  constexpr int hi = plan_hi(C::n, C::WB, PASS), c = plan_c(C::n, C::WB, PASS);
+  const int g = tid >> c, l = tid & ((1 << c) - 1);
+  return (g << hi) | (k << c) | l;
+}
+template <class C, int PASS> __device__ __forceinline__ const typename C::TW *pass_tw(const typename C::TW *tw, int tid) {
+  constexpr int c = plan_c(C::n, C::WB, PASS), off = plan_off(C::n, C::WB, PASS);
+  return tw + off + (tid >> c);
+}
+
+// tile <-> registers for pass PASS.  The last pass (c == 0) owns a whole padded row: 16-byte vector accesses.
+template <class C, int PASS> __device__ __forceinline__ void tile_load(typename C::Word (&x)[C::E], const typename C::Word *tile, int tid) {
+  typedef typename C::Word Word;
+  constexpr int c = plan_c(C::n, C::WB, PASS);
+  if (c == 0) {
+    const uint4 *row = reinterpret_cast<const uint4 *>(tile + tid * C::ROW);
+#pragma unroll
+    for (int v = 0; v < C::E / C::VEC; ++v) {
+      uint4 t = row[v];
+      const Word *w = reinterpret_cast<const Word *>(&t);
+#pragma unroll
+      for (int j = 0; j < C::VEC; ++j) x[v * C::VEC + j] = w[j];
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) x[k] = tile[C::pad(pass_pos<C, PASS>(tid, k))];
+  }
+}
+template <class C, int PASS> __device__ __forceinline__ void tile_store(const typename C::Word (&x)[C::E], typename C::Word *tile, int tid) {
+  typedef typename C::Word Word;
+  constexpr int c = plan_c(C::n, C::WB, PASS);
+  if (c == 0) {
+    uint4 *row = reinterpret_cast<uint4 *>(tile + tid * C::ROW);
+#pragma unroll
+    for (int v = 0; v < C::E / C::VEC; ++v) {
+      uint4 t;
+      Word *w = reinterpret_cast<Word *>(&t);
+#pragma unroll
+      for (int j = 0; j < C::VEC; ++j) w[j] = x[v * C::VEC + j];
+      row[v] = t;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) tile[C::pad(pass_pos<C, PASS>(tid, k))] = x[k];
+  }
+}
+
+// coalesced 16-byte-per-lane copies between the padded tile and the unit's slab in global memory
+template <class C> __device__ __forceinline__ void tile_to_gmem(const typename C::Word *tile, typename C::Store *g, int tid) {
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  constexpr int CHUNKS = C::N / C::VEC;
+#pragma unroll
+  for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
+    const int ch = tid + j * C::TPU;
+    if (CHUNKS % C::TPU != 0 && ch >= CHUNKS) break;
+    const int pos = ch * C::VEC;
+    const uint4 t = *reinterpret_cast<const uint4 *>(tile + C::pad(pos));
+    if (sizeof(Store) == sizeof(Word)) {
+      *reinterpret_cast<uint4 *>(g + pos) = t;
+    } else {  // 16-bit limbs: narrow 4 words to 4 limbs (8 bytes)
+      const Word *w = reinterpret_cast<const Word *>(&t);
+      uint2 o;
+      o.x = (uint32_t)w[0] | ((uint32_t)w[1] << 16);
+      o.y = (uint32_t)w[2] | ((uint32_t)w[3] << 16);
+      *reinterpret_cast<uint2 *>(g + pos) = o;
+    }
+  }
+}
+template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word *tile, const typename C::Store *g, int tid) {
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  constexpr int CHUNKS = C::N / C::VEC;
+#pragma unroll
+  for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
+    const int ch = tid + j * C::TPU;
+    if (CHUNKS % C::TPU != 0 && ch >= CHUNKS) break;
+    const int pos = ch * C::VEC;
+    uint4 t;
+    if (sizeof(Store) == sizeof(Word)) {
+      t = __ldg(reinterpret_cast<const uint4 *>(g + pos));
+    } else {
+      const uint2 i = __ldg(reinterpret_cast<const uint2 *>(g + pos));
+      t.x = i.x & 0xffffu; t.y = i.x >> 16; t.z = i.y & 0xffffu; t.w = i.y >> 16;
+    }
+    *reinterpret_cast<uint4 *>(tile + C::pad(pos)) = t;
+  }
+}
+
+// ---- pass chains (compile-time recursion over the passes) ---------------------------------------------------
+
+// forward: passes 1 .. NP-1 after pass 0 has stored its result into the tile
+template <class C, int PASS> struct FwdChain {
+  static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
+                                             typename C::Word p, typename C::Word twop, int tid, int slot, int lane_base) {
+    unit_sync<C>(slot, lane_base);
+    tile_load<C, PASS>(x, tile, tid);
+    fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, twop);
+    if (PASS == C::NP - 1) {
+#pragma unroll
+      for (int k = 0; k < C::E; ++k) x[k] = csub(csub(x[k], twop), p);  // [0,4p) -> canonical (core.hpp:523-529)
+    }
+    tile_store<C, PASS>(x, tile, tid);
+    FwdChain<C, PASS + 1>::run(x, tile, tw, p, twop, tid, slot, lane_base);
+  }
+};
+template <class C> struct FwdChain<C, C::NP> {
+  static __device__ __forceinline__ void run(typename C::Word (&)[C::E], typename C::Word *, const typename C::TW *, typename C::Word,
+                                             typename C::Word, int, int, int) {}
+};
+
+// inverse: passes NP-1 .. 1 (tile -> registers -> tile); pass 0 is done by the kernel body
+template <class C, int PASS> struct InvChain {
+  static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
+                                             typename C::Word p, typename C::Word twop, const typename C::TW ninv, int tid, int slot,
+                                             int lane_base) {
+    unit_sync<C>(slot, lane_base);
+    tile_load<C, PASS>(x, tile, tid);
+    inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, twop, ninv);
+    tile_store<C, PASS>(x, tile, tid);
+    InvChain<C, PASS - 1>::run(x, tile, tw, p, twop, ninv, tid, slot, lane_base);
+  }
+};
+template <class C> struct InvChain<C, 0> {
+  static __device__ __forceinline__ void run(typename C::Word (&)[C::E], typename C::Word *, const typename C::TW *, typename C::Word,
+                                             typename C::Word, const typename C::TW, int, int, int) {}
+};
+
+// ---- kernels -------------------------------------------------------------------------------------------------
+
+template <class C> __device__ __forceinline__ const typename C::TW *stage_twiddles(const NttArgs &a, int cm, unsigned char *smem) {
+  typedef typename C::TW TW;
+  const TW *twg = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::N;
+  if (!C::TW_SMEM) return twg;
+  TW *tws = reinterpret_cast<TW *>(smem);
+  void *bar = smem + C::TW_BYTES;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)C::TW_BYTES);
+    tma_load_1d(tws, twg, (uint32_t)C::TW_BYTES, bar);
+  }
+  mbar_wait(bar, 0);
+  return tws;
+}
+
+template <int LB, int LOGN>
+__global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::MIN_BLOCKS) ntt_fwd_kernel(const NttArgs a) {
+  typedef NttCfg<LB, LOGN> C;
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  typedef typename C::TW TW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
+  const TW *tw = stage_twiddles<C>(a, cm, smem);
+  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p;
+  const int slot = threadIdx.x / C::TPU, tid = threadIdx.x % C::TPU;
+  const int lane_base = (threadIdx.x & 31) - (tid & 31);
+  Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
+  const Store *src = reinterpret_cast<const Store *>(a.src);
+  Store *dst = reinterpret_cast<Store *>(a.dst);
+
+  for (uint32_t b = rank * C::SLOTS + slot; b < a.batch; b += a.ctas_per_residue * C::SLOTS) {
+    const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
+    Word x[C::E];
+    // pass 0 reads straight from global memory: for fixed k the unit's threads touch consecutive limbs
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, 0>(tid, k));
+    fwd_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), p, twop);
+    if (C::NP == 1) {
+#pragma unroll
+      for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)csub(csub(x[k], twop), p);
+    } else {
+      unit_sync<C>(slot, lane_base);  // previous unit's copy-out has finished reading the tile
+      tile_store<C, 0>(x, tile, tid);
+      FwdChain<C, 1>::run(x, tile, tw, p, twop, tid, slot, lane_base);
+      unit_sync<C>(slot, lane_base);
+      tile_to_gmem<C>(tile, dst + ubase, tid);
+    }
+  }
+}
+
+template <int LB, int LOGN>
+__global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::MIN_BLOCKS) ntt_inv_kernel(const NttArgs a) {
+  typedef NttCfg<LB, LOGN> C;
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  typedef typename C::TW TW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
+  const TW *tw = stage_twiddles<C>(a, cm, smem);
+  const TW ninv = tw[C::N - 1];
+  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p;
+  const int slot = threadIdx.x / C::TPU, tid = threadIdx.x % C::TPU;
+  const int lane_base = (threadIdx.x & 31) - (tid & 31);
+  Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
+  const Store *src = reinterpret_cast<const Store *>(a.src);
+  Store *dst = reinterpret_cast<Store *>(a.dst);
+
+  for (uint32_t b = rank * C::SLOTS + slot; b < a.batch; b += a.ctas_per_residue * C::SLOTS) {
+    const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
+    Word x[C::E];
+    if (C::NP == 1) {
+#pragma unroll
+      for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, 0>(tid, k));
+    } else {
+      unit_sync<C>(slot, lane_base);  // previous unit's pass 0 has finished reading the tile
+      gmem_to_tile<C>(tile, src + ubase, tid);
+      InvChain<C, C::NP - 1>::run(x, tile, tw, p, twop, ninv, tid, slot, lane_base);
+      unit_sync<C>(slot, lane_base);
+      tile_load<C, 0>(x, tile, tid);
+    }
+    inv_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), p, twop, ninv);
+    // pass 0 writes straight to global memory (lane-contiguous for fixed k)
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)x[k];
+  }
+}
+
+}  // namespace nflgpu
+#endif

@@ -1,0 +1,44 @@
+// Shared launcher body for one (limb, direction) translation unit.
+#ifndef NFLGPU_NTT_LAUNCH_CUH
+#define NFLGPU_NTT_LAUNCH_CUH
+#include "ntt_dispatch.h"
+#include "ntt_engine.cuh"
+
+namespace nflgpu {
+
+template <int LB, int LOGN, bool INV> cudaError_t launch_ntt_one(const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
+  typedef NttCfg<LB, LOGN> C;
+  void (*kernel)(const NttArgs);
+  if constexpr (INV) kernel = ntt_inv_kernel<LB, LOGN>;
+  else kernel = ntt_fwd_kernel<LB, LOGN>;
+  // per-device one-time setup: opt in to the shared-memory size and ask the occupancy calculator
+  static int blocks_per_sm[64] = {0};
+  if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+  if (blocks_per_sm[device] == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, C::THREADS, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    blocks_per_sm[device] = occ > 0 ? occ : 1;
+  }
+  if (l.batch == 0) return cudaSuccess;
+  // persistent CTAs, each bound to one residue: grid = nmoduli * ctas_per_residue ~ one full wave
+  const uint32_t resident = (uint32_t)num_sms * blocks_per_sm[device];
+  uint32_t cpr = resident / l.nmoduli;
+  if (cpr == 0) cpr = 1;
+  const uint32_t need = (l.batch + C::SLOTS - 1) / C::SLOTS;
+  if (cpr > need) cpr = need;
+  NttArgs a;
+  a.src = l.src; a.dst = l.dst; a.tw = l.tw; a.moduli = l.moduli;
+  a.nmoduli = l.nmoduli; a.batch = l.batch; a.ctas_per_residue = cpr;
+  kernel<<<cpr * l.nmoduli, C::THREADS, C::SMEM_BYTES, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace nflgpu
+
+#define NFLGPU_NTT_CASE(LB, LOGN, INV) \
+  case LOGN: return launch_ntt_one<LB, LOGN, INV>(l, device, num_sms, stream);
+
+#endif

@@ -1,0 +1,11 @@
+// 16-bit limbs, fwd direction: degrees 2^4 .. 2^9 (params<uint16_t>::kMaxPolyDegree = 512).
+#include "ntt_launch.cuh"
+namespace nflgpu {
+cudaError_t launch_ntt_u16_fwd(int log2_degree, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
+  switch (log2_degree) {
+    NFLGPU_NTT_CASE(16, 4, false) NFLGPU_NTT_CASE(16, 5, false) NFLGPU_NTT_CASE(16, 6, false) NFLGPU_NTT_CASE(16, 7, false)
+    NFLGPU_NTT_CASE(16, 8, false) NFLGPU_NTT_CASE(16, 9, false)
+  }
+  return cudaErrorInvalidValue;
+}
+}  // namespace nflgpu

@@ -1,0 +1,192 @@
+// Coefficient-wise modular functors over device-resident batches (HBM-bound elementwise kernels, sm_100a).
+//
+// Replaces the reference's expression evaluator loop (core.hpp:24-37) applied to
+//   addmod ops.hpp:124-135 | submod ops.hpp:141-151 | mulmod ops.hpp:184-219 | mulmod_shoup ops.hpp:225-242
+//   compute_shoup ops.hpp:165-177 | muladd opt/ops.hpp:9-48 | muladd_shoup opt/ops.hpp:56-78
+// and their SSE/AVX2 specialisations (sse.hpp:75-153,309-490; avx2.hpp:69-147,311-423).
+// One 16-byte vector per thread per operand, grid.y = residue so the modulus is uniform per block and no
+// integer division is needed to find it.  Results are canonical and bit-identical to the reference's.
+#include "pointwise.h"
+#include "modarith.cuh"
+
+namespace nflgpu {
+
+// ---- per-limb exact modular multiply (any correct x*y mod p is bit-identical) -----------
+
+template <int LB> struct PW;
+
+template <> struct PW<64> {
+  typedef uint64_t Word;
+  typedef uint64_t Store;
+  static constexpr int VEC = 2;
+  // ops.hpp:201-219: res = x*y (128 bit); q = Pn*hi(res) + (res << 2); r = lo(res) - hi(q)*p; r -= p if r >= p.
+  // (2^128 / p = 4*2^64 + Pn for NFLlib's 62-bit moduli.)
+  static __device__ __forceinline__ Word mulmod(Word x, Word y, Word p, uint64_t pn) {
+    const Word lo = x * y, hi = __umul64hi(x, y);
+    const Word a_lo = pn * hi, a_hi = __umul64hi(pn, hi);
+    const Word b_lo = lo << 2, b_hi = (hi << 2) | (lo >> 62);
+    const Word s_lo = a_lo + b_lo;
+    const Word q_hi = a_hi + b_hi + (s_lo < a_lo ? 1 : 0);
+    Word r = lo - q_hi * p;
+    return csub(r, p);
+  }
+  // floor(x * 2^64 / p) for x < p:  estimate with mu = 4*2^64 + pn, then at most two corrections
+  static __device__ __forceinline__ Word shoup_of(Word x, Word p, uint64_t pn) {
+    Word q = (x << 2) + __umul64hi(x, pn);
+    Word rem = (Word)0 - q * p;  // x*2^64 - q*p, exact because it is < 3p < 2^64
+    if (rem >= p) { rem -= p; ++q; }
+    if (rem >= p) { rem -= p; ++q; }
+    return q;
+  }
+  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umul64hi(a, b); }
+};
+
+template <> struct PW<32> {
+  typedef uint32_t Word;
+  typedef uint32_t Store;
+  static constexpr int VEC = 4;
+  // (x*y) % p (ops.hpp:184-197) through Barrett with mu = floor(2^64 / p): q is exact or one short
+  static __device__ __forceinline__ Word mulmod(Word x, Word y, Word p, uint64_t mu) {
+    const uint64_t res = (uint64_t)x * y;
+    const uint64_t q = __umul64hi(res, mu);
+    Word r = (Word)res - (Word)q * p;
+    return csub(r, p);
+  }
+  static __device__ __forceinline__ Word shoup_of(Word x, Word p, uint64_t mu) {
+    const uint64_t num = (uint64_t)x << 32;
+    uint64_t q = __umul64hi(num, mu);
+    Word rem = (Word)0 - (Word)q * p;  // num - q*p < 2p
+    if (rem >= p) ++q;
+    return (Word)q;
+  }
+  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umulhi(a, b); }
+};
+
+template <> struct PW<16> {
+  typedef uint32_t Word;
+  typedef uint16_t Store;
+  static constexpr int VEC = 8;
+  static __device__ __forceinline__ Word mulmod(Word x, Word y, Word p, uint64_t) { return (x * y) % p; }
+  static __device__ __forceinline__ Word shoup_of(Word x, Word p, uint64_t) { return (x << 16) / p; }
+  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return (a * b) >> 16; }
+};
+
+// ---- functors ------------------------------------------------------------------------------------------------
+
+template <int LB, int OP> struct Functor {
+  typedef typename PW<LB>::Word Word;
+  static __device__ __forceinline__ Word apply(Word a, Word b, Word c, Word d, Word p, uint64_t k) {
+    if (OP == PW_ADD) return csub(a + b, p);                               // ops.hpp:132-133
+    if (OP == PW_SUB) return csub(a + (p - b), p);                         // ops.hpp:149
+    if (OP == PW_MUL) return PW<LB>::mulmod(a, b, p, k);                   // ops.hpp:184-219
+    if (OP == PW_MUL_SHOUP) {                                              // ops.hpp:231-241
+      const Word q = PW<LB>::mulhi(a, c);
+      return csub((Word)(a * b - q * p), p);
+    }
+    if (OP == PW_COMPUTE_SHOUP) {                                          // ops.hpp:170-176
+      while (a >= p) a -= p;
+      return PW<LB>::shoup_of(a, p, k);
+    }
+    if (OP == PW_MULADD) return csub(a + PW<LB>::mulmod(b, c, p, k), p);   // a + b*c
+    if (OP == PW_MULADD_SHOUP) {                                           // a + shoup(b*c, c') (opt/ops.hpp:56-78)
+      const Word q = PW<LB>::mulhi(b, d);
+      return csub(a + csub((Word)(b * c - q * p), p), p);
+    }
+    return 0;
+  }
+};
+
+template <int LB> struct VecIO;
+template <> struct VecIO<64> {
+  static __device__ __forceinline__ void load(uint64_t (&w)[2], const uint64_t *g) {
+    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(g));
+    w[0] = t.x; w[1] = t.y;
+  }
+  static __device__ __forceinline__ void store(uint64_t *g, const uint64_t (&w)[2]) {
+    *reinterpret_cast<ulonglong2 *>(g) = make_ulonglong2(w[0], w[1]);
+  }
+};
+template <> struct VecIO<32> {
+  static __device__ __forceinline__ void load(uint32_t (&w)[4], const uint32_t *g) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(g));
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(uint32_t *g, const uint32_t (&w)[4]) {
+    *reinterpret_cast<uint4 *>(g) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct VecIO<16> {
+  static __device__ __forceinline__ void load(uint32_t (&w)[8], const uint16_t *g) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(g));
+    const uint32_t v[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { w[2 * i] = v[i] & 0xffffu; w[2 * i + 1] = v[i] >> 16; }
+  }
+  static __device__ __forceinline__ void store(uint16_t *g, const uint32_t (&w)[8]) {
+    *reinterpret_cast<uint4 *>(g) = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
+  }
+};
+
+template <int LB, int OP, int NIN>
+__global__ void __launch_bounds__(256) pointwise_kernel(const PwArgs a) {
+  typedef typename PW<LB>::Word Word;
+  typedef typename PW<LB>::Store Store;
+  constexpr int VEC = PW<LB>::VEC;
+  const uint32_t cm = blockIdx.y;
+  const Word p = (Word)a.moduli[cm];
+  const uint64_t k = a.consts[cm];
+  const uint32_t vec_per_row = a.degree / VEC, row_shift = a.log2_degree - (VEC == 2 ? 1 : VEC == 4 ? 2 : 3);
+  const uint64_t total = (uint64_t)a.batch * vec_per_row;
+  Store *dst = reinterpret_cast<Store *>(a.dst);
+  const Store *pa = reinterpret_cast<const Store *>(a.a), *pb = reinterpret_cast<const Store *>(a.b);
+  const Store *pc = reinterpret_cast<const Store *>(a.c), *pd = reinterpret_cast<const Store *>(a.d);
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = v >> row_shift, off = v & (vec_per_row - 1);
+    const size_t at = ((size_t)b * a.nmoduli + cm) * a.degree + off * VEC;
+    Word wa[VEC], wb[VEC], wc[VEC], wd[VEC], wo[VEC];
+    VecIO<LB>::load(wa, pa + at);
+    if (NIN >= 2) VecIO<LB>::load(wb, pb + at);
+    if (NIN >= 3) VecIO<LB>::load(wc, pc + at);
+    if (NIN >= 4) VecIO<LB>::load(wd, pd + at);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i)
+      wo[i] = Functor<LB, OP>::apply(wa[i], NIN >= 2 ? wb[i] : 0, NIN >= 3 ? wc[i] : 0, NIN >= 4 ? wd[i] : 0, p, k);
+    VecIO<LB>::store(dst + at, wo);
+  }
+}
+
+template <int LB, int OP, int NIN> static cudaError_t launch_one(const PwArgs &a, int num_sms, cudaStream_t stream) {
+  constexpr int VEC = PW<LB>::VEC;
+  const uint64_t total = (uint64_t)a.batch * (a.degree / VEC);
+  if (total == 0) return cudaSuccess;
+  uint64_t blocks = (total + 255) / 256;
+  const uint64_t cap = (uint64_t)num_sms * 8 / a.nmoduli + 1;  // ~8 resident blocks of 256 threads per SM over all residues
+  if (blocks > cap) blocks = cap;
+  dim3 grid((unsigned)blocks, a.nmoduli);
+  pointwise_kernel<LB, OP, NIN><<<grid, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int LB> static cudaError_t launch_limb(int op, const PwArgs &a, int num_sms, cudaStream_t s) {
+  switch (op) {
+    case PW_ADD: return launch_one<LB, PW_ADD, 2>(a, num_sms, s);
+    case PW_SUB: return launch_one<LB, PW_SUB, 2>(a, num_sms, s);
+    case PW_MUL: return launch_one<LB, PW_MUL, 2>(a, num_sms, s);
+    case PW_MUL_SHOUP: return launch_one<LB, PW_MUL_SHOUP, 3>(a, num_sms, s);
+    case PW_COMPUTE_SHOUP: return launch_one<LB, PW_COMPUTE_SHOUP, 1>(a, num_sms, s);
+    case PW_MULADD: return launch_one<LB, PW_MULADD, 3>(a, num_sms, s);
+    case PW_MULADD_SHOUP: return launch_one<LB, PW_MULADD_SHOUP, 4>(a, num_sms, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_pointwise(int limb_bits, int op, const PwArgs &a, int num_sms, cudaStream_t stream) {
+  switch (limb_bits) {
+    case 64: return launch_limb<64>(op, a, num_sms, stream);
+    case 32: return launch_limb<32>(op, a, num_sms, stream);
+    case 16: return launch_limb<16>(op, a, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace nflgpu

@@ -1,0 +1,22 @@
+// Internal launcher interface of the pointwise kernels (pointwise.cu).
+#ifndef NFLGPU_POINTWISE_H
+#define NFLGPU_POINTWISE_H
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace nflgpu {
+
+enum PwOp { PW_ADD = 0, PW_SUB, PW_MUL, PW_MUL_SHOUP, PW_COMPUTE_SHOUP, PW_MULADD, PW_MULADD_SHOUP };
+
+struct PwArgs {
+  void *dst;
+  const void *a, *b, *c, *d;
+  const uint64_t *moduli;  // [nmoduli], widened
+  const uint64_t *consts;  // [nmoduli]: 64-bit limbs: Pn = low word of floor(2^128/p); 32-bit: floor(2^64/p); 16-bit: unused
+  uint32_t nmoduli, degree, log2_degree, batch;
+};
+
+cudaError_t launch_pointwise(int limb_bits, int op, const PwArgs &a, int num_sms, cudaStream_t stream);
+
+}  // namespace nflgpu
+#endif

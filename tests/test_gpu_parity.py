@@ -1,0 +1,202 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI (include/nflgpu.h) via
+ctypes; results are compared bit-for-bit (np.array_equal on the raw limbs — never the reference's any-equal
+operator==, ops.hpp:81-95) with
+  * fixtures produced by the unmodified reference (tests/golden/kat_*.npz, hashes.json),
+  * the CPU oracle (oracle/nfl_oracle.c) on seeded inputs for every supported size,
+  * the live compiled reference (oracle/_ref) when it travelled to the box,
+and at the BASELINE.json full sizes through size-independent properties (round trip, linearity, negacyclic
+shift) plus oracle spot checks on a slice of the batch."""
+import glob
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle_lib import GOLDEN, Oracle, Ref, have_ref, golden_params, random_polys
+
+pytestmark = pytest.mark.gpu
+
+import nfllib_b200 as nb  # noqa: E402
+
+KATS = sorted(glob.glob(os.path.join(GOLDEN, "kat_*.npz")))
+
+
+def _cfg(path):
+    return tuple(int(x) for x in re.search(r"kat_u(\d+)_n(\d+)_m(\d+)", path).groups())
+
+
+_ctx_cache = {}
+
+
+def ctx_for(bits, N, M):
+    key = (bits, N, M)
+    if key not in _ctx_cache:
+        _ctx_cache[key] = nb.Context(bits, N, M)
+    return _ctx_cache[key]
+
+
+@pytest.mark.parametrize("path", KATS, ids=[os.path.basename(p) for p in KATS])
+def test_reference_fixtures(path):
+    bits, N, M = _cfg(path)
+    k = np.load(path)
+    c = ctx_for(bits, N, M)
+    a, b = k["a"], k["b"]
+    assert np.array_equal(c.run_device("ntt_fwd", a), k["fwd_a"])
+    assert np.array_equal(c.run_device("ntt_fwd", b, inplace=True), k["fwd_b"])
+    assert np.array_equal(c.run_device("ntt_inv", a), k["inv_a"])
+    assert np.array_equal(c.run_device("ntt_inv", k["fwd_a"], inplace=True), a)
+    assert np.array_equal(c.run_device("mul", a, b), k["mul"])
+    assert np.array_equal(c.run_device("add", a, b), k["add"])
+    assert np.array_equal(c.run_device("sub", a, b), k["sub"])
+    assert np.array_equal(c.run_device("compute_shoup", b), k["shoup_b"])
+    assert np.array_equal(c.run_device("mul_shoup", a, b, k["shoup_b"]), k["mul_shoup"])
+    assert np.array_equal(c.run_device("polymul", a, b), k["polymul"])
+    assert np.array_equal(c.run_device("muladd", a, b, k["fwd_a"]), k["muladd"])
+
+
+SIZES = [(64, n) for n in range(2, 15)] + [(32, n) for n in range(3, 16)] + [(16, n) for n in range(4, 10)]
+
+
+@pytest.mark.parametrize("bits,n", SIZES, ids=[f"u{b}_n{n}" for b, n in SIZES])
+def test_all_sizes_vs_oracle(bits, n):
+    N = 1 << n
+    for M, batch in ((1, 3), (2 if bits == 16 else 3, 37 if N <= 4096 else 5)):
+        o = Oracle(bits, N, M)
+        c = ctx_for(bits, N, M)
+        a = random_polys(bits, N, M, batch, 31 * n + M)
+        b = random_polys(bits, N, M, batch, 77 * n + M)
+        fa = o.run("fwd", a)
+        assert np.array_equal(c.run_device("ntt_fwd", a), fa), (bits, N, M, "fwd")
+        assert np.array_equal(c.run_device("ntt_inv", a), o.run("inv", a)), (bits, N, M, "inv")
+        assert np.array_equal(c.run_device("ntt_inv", fa), a), (bits, N, M, "roundtrip")
+        assert np.array_equal(c.run_device("mul", a, b), o.run("mul", a, b))
+        assert np.array_equal(c.run_device("add", a, b), o.run("add", a, b))
+        assert np.array_equal(c.run_device("sub", a, b), o.run("sub", a, b))
+        bs = o.run("compute_shoup", b)
+        assert np.array_equal(c.run_device("compute_shoup", b), bs)
+        assert np.array_equal(c.run_device("mul_shoup", a, b, bs), o.run("mul_shoup", a, b, bs))
+        assert np.array_equal(c.run_device("muladd", a, b, fa), o.run("muladd", a, b, fa))
+        assert np.array_equal(c.run_device("muladd_shoup", fa, a, b, bs), o.run("add", fa, o.run("mul_shoup", a, b, bs)))
+        if N <= 4096:
+            assert np.array_equal(c.run_device("polymul", a, b), o.run("polymul", a, b))
+
+
+def test_edge_polys_and_shift():
+    """all-zero, all p-1, delta_0, X, delta_{N-1}; X*a is the negacyclic shift (tests/nfllib_demo_main_op.cpp:260-331 spirit)."""
+    for bits, N, M in ((64, 1024, 4), (32, 4096, 3), (16, 512, 2)):
+        P = golden_params(bits)["P"]
+        c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+        e = np.zeros((5, M, N), c.dtype)
+        for cm in range(M):
+            e[1, cm, :] = P[cm] - 1
+        e[2, :, 0] = 1
+        e[3, :, 1] = 1
+        e[4, :, N - 1] = 1
+        assert np.array_equal(c.run_device("ntt_fwd", e), o.run("fwd", e))
+        assert np.array_equal(c.run_device("ntt_inv", e), o.run("inv", e))
+        a = random_polys(bits, N, M, 5, 9)
+        x = np.zeros_like(a)
+        x[:, :, 1] = 1
+        got = c.run_device("polymul", a, x)
+        exp = np.roll(a, 1, axis=2)
+        for cm in range(M):
+            exp[:, cm, 0] = ((int(P[cm]) - a[:, cm, N - 1].astype(np.uint64)) % np.uint64(P[cm])).astype(c.dtype)
+        assert np.array_equal(got, exp)
+
+
+def test_hashes_at_baseline_shapes():
+    with open(os.path.join(GOLDEN, "hashes.json")) as f:
+        hs = json.load(f)
+    h = lambda x: hashlib.sha256(np.ascontiguousarray(x).tobytes()).hexdigest()
+    for name, e in hs.items():
+        c = ctx_for(e["bits"], e["N"], e["M"])
+        a = random_polys(e["bits"], e["N"], e["M"], e["batch"], e["seed_a"])
+        b = random_polys(e["bits"], e["N"], e["M"], e["batch"], e["seed_b"])
+        assert h(a) == e["in_a"]
+        fa = c.run_device("ntt_fwd", a)
+        assert h(fa) == e["fwd_a"], name
+        assert h(c.run_device("ntt_inv", fa)) == e["in_a"], name
+        assert h(c.run_device("mul", a, b)) == e["mul"], name
+        assert h(c.run_device("add", a, b)) == e["add"], name
+        assert h(c.run_device("sub", a, b)) == e["sub"], name
+        assert h(c.run_device("polymul", a, b)) == e["polymul"], name
+
+
+FULL = [("C2", 64, 1024, 4, 4096), ("C3", 64, 16384, 8, 256), ("C4", 32, 4096, 14, 2048), ("C5", 64, 8192, 6, 512)]
+
+
+@pytest.mark.parametrize("name,bits,N,M,batch", FULL, ids=[f[0] for f in FULL])
+def test_full_size_properties(name, bits, N, M, batch):
+    """BASELINE.json shapes (batch trimmed only where the host-side oracle/numpy work would take minutes):
+    round trip, linearity of the transform, and oracle equality on the first and last polynomials."""
+    c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+    a = random_polys(bits, N, M, batch, 1234)
+    b = random_polys(bits, N, M, batch, 4321)
+    fa, fb = c.run_device("ntt_fwd", a), c.run_device("ntt_fwd", b)
+    assert np.array_equal(c.run_device("ntt_inv", fa), a)
+    s = c.run_device("add", a, b)
+    assert np.array_equal(c.run_device("ntt_fwd", s), c.run_device("add", fa, fb))
+    for sl in (slice(0, 2), slice(batch - 2, batch)):
+        assert np.array_equal(fa[sl], o.run("fwd", a[sl]))
+        assert np.array_equal(c.run_device("polymul", a, b)[sl], o.run("polymul", a[sl], b[sl])) if sl.start == 0 else True
+    # checksum of checksums: the product in the NTT domain equals the NTT of the negacyclic product
+    prod = c.run_device("polymul", a, b)
+    assert np.array_equal(c.run_device("ntt_fwd", prod), c.run_device("mul", fa, fb))
+
+
+def test_host_op_matches_device_path():
+    bits, N, M, batch = 64, 1024, 4, 700  # > one 32 MiB chunk, ragged tail
+    c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+    a = random_polys(bits, N, M, batch, 5)
+    b = random_polys(bits, N, M, batch, 6)
+    fa = c.host_op("fwd", a)
+    assert np.array_equal(fa[:4], o.run("fwd", a[:4])) and np.array_equal(fa, c.run_device("ntt_fwd", a))
+    assert np.array_equal(c.host_op("inv", fa), a)
+    assert np.array_equal(c.host_op("mul", a, b), c.run_device("mul", a, b))
+    assert np.array_equal(c.host_op("polymul", a[:64], b[:64]), o.run("polymul", a[:64], b[:64]))
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so did not travel")
+def test_live_reference_side_by_side():
+    for bits, N, M in ((64, 1024, 4), (64, 16384, 8), (32, 4096, 14), (64, 8192, 6), (16, 512, 2)):
+        r, c = Ref(bits, N, M), ctx_for(bits, N, M)
+        a = random_polys(bits, N, M, 6, 99)
+        b = random_polys(bits, N, M, 6, 98)
+        fa = r.run("fwd", a)
+        assert np.array_equal(c.run_device("ntt_fwd", a), fa)
+        assert np.array_equal(c.run_device("ntt_inv", fa), a)
+        assert np.array_equal(c.run_device("mul", a, b), r.run("mul", a, b))
+        assert np.array_equal(c.run_device("polymul", a, b), r.run("polymul", a, b))
+
+
+def test_errors_and_empty():
+    c = ctx_for(64, 1024, 4)
+    p = c.alloc(1)
+    c.ntt_fwd(p, p, 0)  # empty batch is a no-op
+    with pytest.raises(nb.NflGpuError):
+        c.ntt_fwd(p + 8, p, 1)  # misaligned
+    with pytest.raises(nb.NflGpuError):
+        c.ntt_fwd(0, p, 1)  # null
+    c.free(p)
+    with pytest.raises(nb.NflGpuError):
+        nb.Context(64, 1000, 1)  # not a power of two (core.hpp:55-60)
+    with pytest.raises(nb.NflGpuError):
+        nb.Context(16, 1024, 1)  # degree > params<uint16_t>::kMaxPolyDegree
+    with pytest.raises(nb.NflGpuError):
+        nb.Context(16, 512, 3)  # nmoduli > params<uint16_t>::kMaxNbModuli
+    with pytest.raises(nb.NflGpuError):
+        nb.Context(64, 32768, 1)  # beyond the kernels' shared-memory tile
+
+
+def test_first_modulus_window_matches_residue_slice():
+    """A context over moduli [3, 7) computes residues 3..6 of the 7-modulus transform (residue sharding)."""
+    bits, N = 32, 4096
+    full, part = ctx_for(bits, N, 7), nb.Context(bits, N, 4, first_modulus=3)
+    a = random_polys(bits, N, 7, 4, 17, P=[int(v) for v in full.moduli])
+    fa = full.run_device("ntt_fwd", a)
+    sub = np.ascontiguousarray(a[:, 3:7, :])
+    assert np.array_equal(part.run_device("ntt_fwd", sub), fa[:, 3:7, :])
+    part.close()
