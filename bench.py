@@ -82,7 +82,7 @@ def cpu_sample(polys):
 
 def cpu_baseline(target_seconds=12.0):
     kind, eng, flags = cpu_engine()
-    threads = (os.cpu_count() or 1) if kind == "reference" else 1
+    threads = usable_cpus() if kind == "reference" else 1
     polys = 512 * threads if kind == "reference" else 64
     a, work = cpu_sample(polys)
     cpu_pass(kind, eng, a, work, threads)  # warm-up (page faults, static tables)
@@ -98,6 +98,19 @@ def cpu_baseline(target_seconds=12.0):
             "sample": f"{reps} x (ntt_pow_phi + invntt_pow_invphi) over {polys} seeded polys of the same shape, {threads} host threads, "
                       f"{dt:.1f} s; build: {flags}",
             "host_cpu": host_cpu()}
+
+
+def usable_cpus():
+    """host threads this process may really use: affinity mask capped by the cgroup v2 cpu.max quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
 
 
 def host_cpu():
@@ -116,7 +129,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     kind, eng, flags = cpu_engine()
-    threads = (os.cpu_count() or 1) if kind == "reference" else 1
+    threads = usable_cpus() if kind == "reference" else 1
     polys = 256 * threads if kind == "reference" else 32  # bounded sample per step
     a, work = cpu_sample(polys)
     for _ in range(args.warmup):

@@ -1,0 +1,453 @@
+// nfl_b200.hpp — C++11 host surface of the B200-native NFLlib hot path.
+//
+// Keeps the reference's template surface for the NTT / pointwise path so user code written against
+// <nfl.hpp> keeps compiling for that path:
+//     nfl::poly<T, Degree, NbModuli>          include/nfl/poly.hpp:82-309   (same POD layout, 32-byte aligned)
+//     .ntt_pow_phi() / .invntt_pow_invphi()   poly.hpp:167-168
+//     operator+ - * == !=, shoup(), compute_shoup()   poly.hpp:346-352, ops.hpp:18-45 (lazy expressions)
+//     nfl::add / sub / mul, poly_from_modulus          poly.hpp:314-337
+//     nfl::params<T>                                   params.hpp (tables re-derived by libnflgpu)
+// but evaluates on the GPU through the C ABI of include/nflgpu.h (the only thing this header links against).
+// Error convention follows the reference: std::runtime_error (core.hpp:111-115) — every nonzero nflgpu status
+// is converted to one.  There is no CPU fallback: without libnflgpu + a CUDA device the calls throw.
+//
+// A single host-resident poly per call is PCIe-bound (hard part 5); throughput code should
+// use nfl::cuda::batch<poly> below, which keeps `count` polys resident in HBM between operations.
+//
+// Out of scope here: samplers other than a test-grade uniform(), GMP lifting, poly_p,
+// serialization (the byte layout is identical, so reference-serialized polys can be memcpy'd in).
+#ifndef NFL_B200_HPP
+#define NFL_B200_HPP
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <initializer_list>
+#include <iostream>
+#include <iterator>
+#include <memory>
+#include <new>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "nflgpu.h"
+
+namespace nfl {
+
+// ---------------------------------------------------------------------------------------------------------
+// params<T>  (params.hpp:12-119).  The tables are fetched once from libnflgpu's derivation.
+// ---------------------------------------------------------------------------------------------------------
+namespace detail {
+
+inline void check(int rc, const char *what) {
+  if (rc != 0) throw std::runtime_error(std::string("nfl_b200: ") + what + ": " + nflgpu_last_error());
+}
+
+template <class T> struct limb_traits;
+template <> struct limb_traits<uint16_t> {
+  typedef int16_t signed_type; typedef uint32_t greater_type;
+  static constexpr int bits = 16; static constexpr unsigned max_moduli = 2; static constexpr unsigned max_degree = 512;
+};
+template <> struct limb_traits<uint32_t> {
+  typedef int32_t signed_type; typedef uint64_t greater_type;
+  static constexpr int bits = 32; static constexpr unsigned max_moduli = 291; static constexpr unsigned max_degree = 32768;
+};
+template <> struct limb_traits<uint64_t> {
+  typedef int64_t signed_type; typedef unsigned __int128 greater_type;
+  static constexpr int bits = 64; static constexpr unsigned max_moduli = 1000; static constexpr unsigned max_degree = 1048576;
+};
+
+template <class T> struct param_tables {
+  std::vector<uint64_t> P, Pn, roots, invkmax;
+  param_tables() {
+    const size_t n = limb_traits<T>::max_moduli;
+    P.resize(n); Pn.resize(n); roots.resize(n); invkmax.resize(n);
+    // roots of all 1000 64-bit moduli take a moment to derive; fetch P/Pn/invkmax eagerly, roots lazily
+    check(nflgpu_params(limb_traits<T>::bits, 0, n, P.data(), Pn.data(), nullptr, invkmax.data()), "nflgpu_params");
+    std::fill(roots.begin(), roots.end(), 0);
+  }
+  static param_tables &get() { static param_tables t; return t; }
+  uint64_t root(size_t i) {
+    if (!roots[i]) check(nflgpu_params(limb_traits<T>::bits, i, 1, nullptr, nullptr, &roots[i], nullptr), "nflgpu_params");
+    return roots[i];
+  }
+};
+
+template <class T, int WHICH> struct param_view {  // params<T>::P[i] syntax
+  T operator[](size_t i) const {
+    param_tables<T> &t = param_tables<T>::get();
+    return static_cast<T>(WHICH == 0 ? t.P[i] : WHICH == 1 ? t.Pn[i] : WHICH == 2 ? t.root(i) : t.invkmax[i]);
+  }
+};
+
+}  // namespace detail
+
+template <class T> struct params {
+  typedef T value_type;
+  typedef typename detail::limb_traits<T>::signed_type signed_value_type;
+  typedef typename detail::limb_traits<T>::greater_type greater_value_type;
+  typedef value_type *poly_t;
+  static constexpr unsigned int kMaxNbModuli = detail::limb_traits<T>::max_moduli;
+  static constexpr unsigned int kModulusBitsize = detail::limb_traits<T>::bits - 2;
+  static constexpr unsigned int kModulusRepresentationBitsize = detail::limb_traits<T>::bits;
+  static constexpr unsigned int kMaxPolyDegree = detail::limb_traits<T>::max_degree;
+  static const detail::param_view<T, 0> P;
+  static const detail::param_view<T, 1> Pn;
+  static const detail::param_view<T, 2> primitive_roots;
+  static const detail::param_view<T, 3> invkMaxPolyDegree;
+};
+template <class T> const detail::param_view<T, 0> params<T>::P = {};
+template <class T> const detail::param_view<T, 1> params<T>::Pn = {};
+template <class T> const detail::param_view<T, 2> params<T>::primitive_roots = {};
+template <class T> const detail::param_view<T, 3> params<T>::invkMaxPolyDegree = {};
+template <class T> constexpr unsigned int params<T>::kMaxNbModuli;
+template <class T> constexpr unsigned int params<T>::kModulusBitsize;
+template <class T> constexpr unsigned int params<T>::kModulusRepresentationBitsize;
+template <class T> constexpr unsigned int params<T>::kMaxPolyDegree;
+
+// The reference's backend seam is the SIMD tag chosen by CC_SIMD (arch.hpp:6-18); this backend's tag:
+namespace simd { struct cuda {}; }
+#define CC_SIMD nfl::simd::cuda
+
+struct uniform {};  // poly.hpp:42 — test-grade here (std::mt19937_64), NOT the reference's Salsa20 stream
+
+template <class T, size_t Degree, size_t NbModuli> class poly;
+
+// ---------------------------------------------------------------------------------------------------------
+// Backend: one nflgpu context per (T, Degree, NbModuli), created on first use (the reference builds its
+// tables at static-init time, core.hpp:45-62).  Device ordinal: environment variable NFL_B200_DEVICE (default 0).
+// ---------------------------------------------------------------------------------------------------------
+namespace detail {
+
+template <class T, size_t Degree, size_t NbModuli> struct backend {
+  nflgpu_ctx *ctx;
+  backend() : ctx(nullptr) {
+    static_assert(Degree <= limb_traits<T>::max_degree, "degree > params<T>::kMaxPolyDegree");    // core.hpp:59-60
+    static_assert(NbModuli <= limb_traits<T>::max_moduli, "nmoduli > params<T>::kMaxNbModuli");   // core.hpp:57-58
+    static_assert((Degree & (Degree - 1)) == 0 && Degree * sizeof(T) >= 32, "degree must be a power of two, >= 32 bytes of limbs");
+    const char *dev = std::getenv("NFL_B200_DEVICE");
+    check(nflgpu_ctx_create(&ctx, limb_traits<T>::bits, Degree, NbModuli, 0, dev ? std::atoi(dev) : 0, nullptr, nullptr),
+          "nflgpu_ctx_create");
+  }
+  ~backend() { nflgpu_ctx_destroy(ctx); }
+  static backend &get() { static backend b; return b; }
+};
+
+// RAII device buffer of `count` polys
+template <class P> struct dev_buf {
+  void *p; size_t count;
+  explicit dev_buf(size_t n) : p(nullptr), count(n) { check(nflgpu_alloc(P::backend_type::get().ctx, n, &p), "nflgpu_alloc"); }
+  ~dev_buf() { if (p) nflgpu_free(P::backend_type::get().ctx, p); }
+  dev_buf(const dev_buf &) = delete;
+  dev_buf &operator=(const dev_buf &) = delete;
+};
+
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------------------
+// Expression templates (ops.hpp:47-277).  Nodes are evaluated on the device: leaves are uploaded, every functor
+// is one kernel, `shoup(a*b, b')` is rewritten to mulmod_shoup (ops.hpp:266-277) and `x + y*z` to the fused muladd.
+// ---------------------------------------------------------------------------------------------------------
+namespace ops {
+
+struct addmod {}; struct submod {}; struct mulmod {}; struct shoup {}; struct mulmod_shoup {}; struct compute_shoup {};
+struct eqmod {}; struct neqmod {};
+
+template <class Op, class... Args> struct expr {
+  typedef typename std::tuple_element<0, std::tuple<Args...>>::type first_arg;
+  typedef typename first_arg::poly_type poly_type;
+  std::tuple<Args const &...> args;
+  explicit expr(Args const &... a) : args(a...) {}
+  // the reference's semantics: `==` is true iff ANY coefficient is equal, `!=` iff ANY differs (ops.hpp:81-95)
+  explicit operator bool() const;
+};
+
+}  // namespace ops
+
+namespace detail {
+
+template <class P> struct eval;  // forward
+
+// evaluates any operand (poly or expr) into a fresh device buffer of one poly
+template <class P, class X> struct operand_eval;
+template <class P> struct operand_eval<P, P> {
+  static std::unique_ptr<dev_buf<P>> run(P const &x) {
+    std::unique_ptr<dev_buf<P>> b(new dev_buf<P>(1));
+    check(nflgpu_upload(P::backend_type::get().ctx, b->p, x.data(), 1, nullptr), "nflgpu_upload");
+    return b;
+  }
+};
+
+#define NFLB200_BIN(OPTAG, CALL)                                                                                    \
+  template <class P, class A0, class A1> struct operand_eval<P, ops::expr<ops::OPTAG, A0, A1>> {                   \
+    static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::OPTAG, A0, A1> const &e) {                               \
+      auto a = operand_eval<P, A0>::run(std::get<0>(e.args));                                                       \
+      auto b = operand_eval<P, A1>::run(std::get<1>(e.args));                                                       \
+      check(CALL(P::backend_type::get().ctx, a->p, a->p, b->p, 1, nullptr), #CALL);                                \
+      return a;                                                                                                     \
+    }                                                                                                               \
+  };
+NFLB200_BIN(submod, nflgpu_sub)
+NFLB200_BIN(mulmod, nflgpu_mul)
+#undef NFLB200_BIN
+
+// x + y  — with the fused form when y is a product (core.hpp:24-37 evaluates the whole tree in one pass)
+template <class P, class A0, class A1> struct operand_eval<P, ops::expr<ops::addmod, A0, A1>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::addmod, A0, A1> const &e) {
+    auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
+    auto b = operand_eval<P, A1>::run(std::get<1>(e.args));
+    check(nflgpu_add(P::backend_type::get().ctx, a->p, a->p, b->p, 1, nullptr), "nflgpu_add");
+    return a;
+  }
+};
+template <class P, class A0, class B0, class B1> struct operand_eval<P, ops::expr<ops::addmod, A0, ops::expr<ops::mulmod, B0, B1>>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::addmod, A0, ops::expr<ops::mulmod, B0, B1>> const &e) {
+    auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
+    auto const &m = std::get<1>(e.args);
+    auto b = operand_eval<P, B0>::run(std::get<0>(m.args));
+    auto c = operand_eval<P, B1>::run(std::get<1>(m.args));
+    check(nflgpu_muladd(P::backend_type::get().ctx, a->p, a->p, b->p, c->p, 1, nullptr), "nflgpu_muladd");
+    return a;
+  }
+};
+template <class P, class A0, class A1, class A2> struct operand_eval<P, ops::expr<ops::mulmod_shoup, A0, A1, A2>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::mulmod_shoup, A0, A1, A2> const &e) {
+    auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
+    auto b = operand_eval<P, A1>::run(std::get<1>(e.args));
+    auto c = operand_eval<P, A2>::run(std::get<2>(e.args));
+    check(nflgpu_mul_shoup(P::backend_type::get().ctx, a->p, a->p, b->p, c->p, 1, nullptr), "nflgpu_mul_shoup");
+    return a;
+  }
+};
+template <class P, class A0> struct operand_eval<P, ops::expr<ops::compute_shoup, A0>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::compute_shoup, A0> const &e) {
+    auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
+    check(nflgpu_compute_shoup(P::backend_type::get().ctx, a->p, a->p, 1, nullptr), "nflgpu_compute_shoup");
+    return a;
+  }
+};
+
+template <class X> struct is_operand : std::false_type {};
+template <class T, size_t D, size_t M> struct is_operand<poly<T, D, M>> : std::true_type {};
+template <class Op, class... A> struct is_operand<ops::expr<Op, A...>> : std::true_type {};
+
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------------------
+// poly  (poly.hpp:82-309)
+// ---------------------------------------------------------------------------------------------------------
+template <class T, size_t Degree, size_t NbModuli> class poly {
+  static constexpr size_t N = Degree * NbModuli;
+  T _data[N] __attribute__((aligned(32)));
+
+public:
+  typedef poly poly_type;
+  typedef detail::backend<T, Degree, NbModuli> backend_type;
+  using value_type = typename params<T>::value_type;
+  using greater_value_type = typename params<T>::greater_value_type;
+  using signed_value_type = typename params<T>::signed_value_type;
+  using pointer_type = T *;
+  using const_pointer_type = T const *;
+  using iterator = pointer_type;
+  using const_iterator = const_pointer_type;
+  using simd_mode = CC_SIMD;
+  static constexpr size_t degree = Degree;
+  static constexpr size_t nmoduli = NbModuli;
+  static constexpr size_t nbits = params<T>::kModulusBitsize;
+  static constexpr size_t aggregated_modulus_bit_size = NbModuli * nbits;
+
+  /* constructors (core.hpp:64-147) */
+  poly() { set(value_type(0)); }
+  poly(uniform const &mode) { set(mode); }
+  poly(value_type v, bool reduce_coeffs = true) { set(v, reduce_coeffs); }
+  poly(std::initializer_list<value_type> values, bool reduce_coeffs = true) { set(values.begin(), values.end(), reduce_coeffs); }
+  template <class It> poly(It first, It last, bool reduce_coeffs = true) { set(first, last, reduce_coeffs); }
+  template <class Op, class... Args> poly(ops::expr<Op, Args...> const &e) { *this = e; }
+
+  /* set() (core.hpp:76-147): coefficient v (resp. the list) replicated over the residues, reduced mod p_cm */
+  void set(value_type v, bool reduce_coeffs = true) {
+    if (v == 0) { std::memset(_data, 0, sizeof(_data)); return; }
+    for (size_t cm = 0; cm < nmoduli; ++cm) {
+      _data[cm * degree] = reduce_coeffs ? static_cast<T>(v % get_modulus(cm)) : v;
+      std::fill(_data + cm * degree + 1, _data + (cm + 1) * degree, T(0));
+    }
+  }
+  void set(std::initializer_list<value_type> values, bool reduce_coeffs = true) { set(values.begin(), values.end(), reduce_coeffs); }
+  template <class It> void set(It first, It last, bool reduce_coeffs = true) {
+    // core.hpp:100-147: either `degree` values (replicated into every residue) or degree*nmoduli values
+    const size_t size = std::distance(first, last);
+    if (size > degree && size != degree * nmoduli)
+      throw std::runtime_error("poly: CRITICAL, initializer of size above degree but not equal to nmoduli*degree");  // core.hpp:111-115
+    for (size_t cm = 0; cm < nmoduli; ++cm) {
+      It it = first;
+      if (size == degree * nmoduli) std::advance(it, cm * degree);
+      size_t i = 0;
+      for (; i < degree && it != last && i < size; ++i, ++it)
+        _data[cm * degree + i] = reduce_coeffs ? static_cast<T>(static_cast<value_type>(*it) % get_modulus(cm)) : static_cast<T>(*it);
+      for (; i < degree; ++i) _data[cm * degree + i] = 0;
+    }
+  }
+  void set(uniform const &) {
+    static std::mt19937_64 gen((std::random_device())());
+    for (size_t cm = 0; cm < nmoduli; ++cm)
+      for (size_t i = 0; i < degree; ++i) _data[cm * degree + i] = static_cast<T>(gen() % get_modulus(cm));
+  }
+
+  /* assignment */
+  poly &operator=(value_type v) { set(v); return *this; }
+  poly &operator=(uniform const &mode) { set(mode); return *this; }
+  poly &operator=(std::initializer_list<value_type> values) { set(values); return *this; }
+  template <class Op, class... Args> poly &operator=(ops::expr<Op, Args...> const &e) {  // core.hpp:24-37
+    auto r = detail::operand_eval<poly, ops::expr<Op, Args...>>::run(e);
+    nflgpu_ctx *ctx = backend_type::get().ctx;
+    detail::check(nflgpu_download(ctx, _data, r->p, 1, nullptr), "nflgpu_download");
+    detail::check(nflgpu_sync(ctx, nullptr), "nflgpu_sync");
+    return *this;
+  }
+
+  /* iterators, indexing, misc (poly.hpp:141-163) */
+  iterator begin() { return _data; }
+  iterator end() { return _data + N; }
+  const_iterator begin() const { return _data; }
+  const_iterator end() const { return _data + N; }
+  const_iterator cbegin() const { return _data; }
+  const_iterator cend() const { return _data + N; }
+  value_type const &operator()(size_t cm, size_t i) const { return _data[cm * degree + i]; }
+  value_type &operator()(size_t cm, size_t i) { return _data[cm * degree + i]; }
+  pointer_type data() { return _data; }
+  const_pointer_type data() const { return _data; }
+  static value_type get_modulus(size_t n) { return params<T>::P[n]; }
+
+  /* NTT — public API (poly.hpp:167-168); one host poly per call: H2D + kernel + D2H inside libnflgpu */
+  void ntt_pow_phi() { detail::check(nflgpu_host_op(backend_type::get().ctx, 0, _data, _data, nullptr, nullptr, 1), "ntt_pow_phi"); }
+  void invntt_pow_invphi() { detail::check(nflgpu_host_op(backend_type::get().ctx, 1, _data, _data, nullptr, nullptr, 1), "invntt_pow_invphi"); }
+
+  /* manual serializers (poly.hpp:180-185): identical byte layout */
+  void serialize_manually(std::ostream &os) { os.write(reinterpret_cast<char *>(_data), N * sizeof(T)); }
+  void deserialize_manually(std::istream &is) { is.read(reinterpret_cast<char *>(_data), N * sizeof(T)); }
+} __attribute__((aligned(32)));
+
+template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::degree;
+template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::nmoduli;
+template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::nbits;
+template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::aggregated_modulus_bit_size;
+
+/* operator overloads (poly.hpp:346-352 via the macros of ops.hpp:18-45) */
+#define NFLB200_DECLARE_BINARY(NAME, TAG)                                                                                   \
+  template <class A0, class A1>                                                                                             \
+  typename std::enable_if<detail::is_operand<A0>::value && detail::is_operand<A1>::value, ops::expr<ops::TAG, A0, A1>>::type \
+  NAME(A0 const &a, A1 const &b) { return ops::expr<ops::TAG, A0, A1>(a, b); }
+NFLB200_DECLARE_BINARY(operator-, submod)
+NFLB200_DECLARE_BINARY(operator+, addmod)
+NFLB200_DECLARE_BINARY(operator*, mulmod)
+NFLB200_DECLARE_BINARY(operator==, eqmod)
+NFLB200_DECLARE_BINARY(operator!=, neqmod)
+#undef NFLB200_DECLARE_BINARY
+
+// shoup(a * b, bprime)  ->  mulmod_shoup(a, b, bprime)   (ops.hpp:266-277)
+template <class A0, class A1, class A2>
+ops::expr<ops::mulmod_shoup, A0, A1, A2> shoup(ops::expr<ops::mulmod, A0, A1> const &prod, A2 const &bprime) {
+  return ops::expr<ops::mulmod_shoup, A0, A1, A2>(std::get<0>(prod.args), std::get<1>(prod.args), bprime);
+}
+template <class A0> typename std::enable_if<detail::is_operand<A0>::value, ops::expr<ops::compute_shoup, A0>>::type compute_shoup(A0 const &a) {
+  return ops::expr<ops::compute_shoup, A0>(a);
+}
+
+namespace detail {
+// heap storage for one over-aligned poly (plain `new` does not honour 32-byte alignment in C++11;
+// the reference has the same caveat, tests/nfllib_demo_main_func.cpp:40-45)
+template <class P> struct aligned_holder {
+  P *p;
+  aligned_holder() : p(nullptr) {
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 32, sizeof(P)) != 0) throw std::bad_alloc();
+    p = new (raw) P;
+  }
+  ~aligned_holder() { if (p) { p->~P(); free(p); } }
+  aligned_holder(const aligned_holder &) = delete;
+  aligned_holder &operator=(const aligned_holder &) = delete;
+};
+// materialise an operand on the host (used only by the boolean comparisons, which are not on the hot path)
+template <class P> P const &host_value(P const &p, P &) { return p; }
+template <class P, class Op, class... A> P const &host_value(ops::expr<Op, A...> const &e, P &tmp) { tmp = e; return tmp; }
+}  // namespace detail
+
+namespace ops {
+template <class Op, class... Args> expr<Op, Args...>::operator bool() const {
+  static_assert(std::is_same<Op, eqmod>::value || std::is_same<Op, neqmod>::value, "only == and != convert to bool (ops.hpp:81-95)");
+  typedef poly_type P;
+  detail::aligned_holder<P> ta, tb;
+  P const &a = detail::host_value<P>(std::get<0>(args), *ta.p);
+  P const &b = detail::host_value<P>(std::get<1>(args), *tb.p);
+  const bool want_equal = std::is_same<Op, eqmod>::value;
+  for (size_t i = 0; i < P::degree * P::nmoduli; ++i)
+    if ((a.begin()[i] == b.begin()[i]) == want_equal) return true;  // ANY coefficient (the reference's semantics)
+  return false;
+}
+}  // namespace ops
+
+/* High level wrappers (poly.hpp:314-332) and the modulus-size alias (poly.hpp:336-337) */
+template <class T, size_t D, size_t M> void sub(poly<T, D, M> &out, poly<T, D, M> const &a, poly<T, D, M> const &b) { out = a - b; }
+template <class T, size_t D, size_t M> void add(poly<T, D, M> &out, poly<T, D, M> const &a, poly<T, D, M> const &b) { out = a + b; }
+template <class T, size_t D, size_t M> void mul(poly<T, D, M> &out, poly<T, D, M> const &a, poly<T, D, M> const &b) { out = a * b; }
+template <class T, size_t Degree, size_t AggregatedModulusBitSize>
+using poly_from_modulus = poly<T, Degree, AggregatedModulusBitSize / params<T>::kModulusBitsize>;
+
+/* stream operator (core.hpp:398-421): "{ c0U, c1U, ... }" per residue */
+template <class T, size_t D, size_t M> std::ostream &operator<<(std::ostream &os, poly<T, D, M> const &p) {
+  os << "{ ";
+  for (size_t i = 0; i < D * M; ++i) os << (i ? ", " : "") << static_cast<uint64_t>(p.begin()[i]) << "U";
+  return os << " }";
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident batches: the throughput API.  `count` polys stay in HBM in exactly the layout of poly[count].
+// ---------------------------------------------------------------------------------------------------------
+namespace cuda {
+
+template <class P> class batch {
+  detail::dev_buf<P> buf_;
+  static nflgpu_ctx *ctx() { return P::backend_type::get().ctx; }
+
+public:
+  explicit batch(size_t count) : buf_(count) {}
+  batch(P const *host, size_t count) : buf_(count) { upload(host); }
+  size_t size() const { return buf_.count; }
+  void *device_ptr() { return buf_.p; }
+  const void *device_ptr() const { return buf_.p; }
+  void upload(P const *host) { detail::check(nflgpu_upload(ctx(), buf_.p, host, buf_.count, nullptr), "nflgpu_upload"); sync(); }
+  void download(P *host) const { detail::check(nflgpu_download(ctx(), host, buf_.p, buf_.count, nullptr), "nflgpu_download"); sync(); }
+  static void sync() { detail::check(nflgpu_sync(ctx(), nullptr), "nflgpu_sync"); }
+
+  void ntt_pow_phi() { detail::check(nflgpu_ntt_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_fwd"); }
+  void invntt_pow_invphi() { detail::check(nflgpu_ntt_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_inv"); }
+
+#define NFLB200_BATCH_BIN(NAME, CALL)                                                                                       \
+  void NAME(batch const &a, batch const &b) {                                                                               \
+    if (a.size() != size() || b.size() != size()) throw std::runtime_error("nfl::cuda::batch: size mismatch");             \
+    detail::check(CALL(ctx(), buf_.p, a.buf_.p, b.buf_.p, buf_.count, nullptr), #CALL);                                    \
+  }
+  NFLB200_BATCH_BIN(assign_add, nflgpu_add)          // *this = a + b
+  NFLB200_BATCH_BIN(assign_sub, nflgpu_sub)          // *this = a - b
+  NFLB200_BATCH_BIN(assign_mul, nflgpu_mul)          // *this = a * b
+  NFLB200_BATCH_BIN(assign_polymul, nflgpu_polymul)  // *this = invntt(ntt(a) * ntt(b))
+#undef NFLB200_BATCH_BIN
+  void assign_compute_shoup(batch const &a) { detail::check(nflgpu_compute_shoup(ctx(), buf_.p, a.buf_.p, buf_.count, nullptr), "nflgpu_compute_shoup"); }
+  void assign_mul_shoup(batch const &a, batch const &b, batch const &bprime) {
+    detail::check(nflgpu_mul_shoup(ctx(), buf_.p, a.buf_.p, b.buf_.p, bprime.buf_.p, buf_.count, nullptr), "nflgpu_mul_shoup");
+  }
+  void assign_muladd(batch const &a, batch const &b, batch const &c) {  // *this = a + b * c
+    detail::check(nflgpu_muladd(ctx(), buf_.p, a.buf_.p, b.buf_.p, c.buf_.p, buf_.count, nullptr), "nflgpu_muladd");
+  }
+};
+
+}  // namespace cuda
+}  // namespace nfl
+
+#endif  // NFL_B200_HPP

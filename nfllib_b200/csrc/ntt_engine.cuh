@@ -51,10 +51,17 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int PADW = VEC;                      // 16 bytes of padding per row of E words
   static constexpr int ROW = E + PADW;
   static constexpr int TILE_WORDS = (NP > 1) ? (N >> e) * ROW : 0;
-  static constexpr int TARGET_THREADS = 256;
+#ifndef NFLGPU_TARGET_THREADS
+#define NFLGPU_TARGET_THREADS 256
+#endif
+  static constexpr int TARGET_THREADS = NFLGPU_TARGET_THREADS;
   static constexpr int SLOTS = (TPU >= TARGET_THREADS) ? 1 : TARGET_THREADS / TPU;
   static constexpr int THREADS = TPU * SLOTS;
+#ifdef NFLGPU_MIN_BLOCKS
+  static constexpr int MIN_BLOCKS = NFLGPU_MIN_BLOCKS;
+#else
   static constexpr int MIN_BLOCKS = (THREADS <= 256) ? 2 : 1;
+#endif
   static constexpr bool TW_SMEM = (size_t)N * sizeof(TW) <= 32768;
   static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)N * sizeof(TW) : 0;
   static constexpr size_t SMEM_BYTES = TW_BYTES + 16 /* mbarrier */ + (size_t)SLOTS * TILE_WORDS * sizeof(Word);

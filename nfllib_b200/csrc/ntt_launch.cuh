@@ -38,7 +38,13 @@ template <int LB, int LOGN, bool INV> cudaError_t launch_ntt_one(const NttLaunch
 
 }  // namespace nflgpu
 
+// NFLGPU_ONLY_LOGN restricts the instantiations to one size (fast experiment builds, tools/variants.sh)
+#ifdef NFLGPU_ONLY_LOGN
+#define NFLGPU_NTT_CASE(LB, LOGN, INV) \
+  case LOGN: if constexpr (LOGN == NFLGPU_ONLY_LOGN) return launch_ntt_one<LB, LOGN, INV>(l, device, num_sms, stream); else break;
+#else
 #define NFLGPU_NTT_CASE(LB, LOGN, INV) \
   case LOGN: return launch_ntt_one<LB, LOGN, INV>(l, device, num_sms, stream);
+#endif
 
 #endif

@@ -27,7 +27,14 @@
 namespace nflgpu {
 
 // Largest radix exponent per thread: 32 coefficients of 64 bits or 64 of 32 bits = 64 data registers.
-NFLGPU_HD constexpr int plan_emax(int word_bits) { return word_bits == 64 ? 5 : 6; }
+// (NFLGPU_EMAX64 / NFLGPU_EMAX32 are tuning overrides used by tools/variants.sh experiments.)
+#ifndef NFLGPU_EMAX64
+#define NFLGPU_EMAX64 5
+#endif
+#ifndef NFLGPU_EMAX32
+#define NFLGPU_EMAX32 6
+#endif
+NFLGPU_HD constexpr int plan_emax(int word_bits) { return word_bits == 64 ? NFLGPU_EMAX64 : NFLGPU_EMAX32; }
 NFLGPU_HD constexpr int plan_npass(int n, int word_bits) { return (n + plan_emax(word_bits) - 1) / plan_emax(word_bits); }
 NFLGPU_HD constexpr int plan_e(int n, int word_bits) { return (n + plan_npass(n, word_bits) - 1) / plan_npass(n, word_bits); }
 // stages in pass i (only the first pass may be short)
