@@ -20,12 +20,15 @@ template <> struct Arith<64> {
   static constexpr int WORD_BITS = 64;
   static __device__ __forceinline__ Word tw_w(const TW &t) { return t.x; }
   static __device__ __forceinline__ Word tw_ws(const TW &t) { return t.y; }
-  // y*w - floor(y*ws / 2^64)*p  in [0, 2p) for any 64-bit y  (algos.hpp:37-38)
-  static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word p) {
-    Word q = __umul64hi(y, ws);
-    return y * w - q * p;
-  }
+  // (measured, profiles/r01b_*: on sm_100 IMAD.WIDE.U32 holds the fmaheavy pipe 4 cycles per warp, IMAD.HI.U32 ~6 and a
+  //  plain IMAD 2, so the four IMAD.WIDE of __umul64hi are cheaper than any formulation using IMAD.HI.)
   static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umul64hi(a, b); }
+  // y*w - floor(y*ws / 2^64)*p  in [0, 2p) for any 64-bit y  (algos.hpp:37-38).  `np` is -p mod 2^64 (kept opaque
+  // to the optimiser by the caller) so the whole right-hand side is one multiply-accumulate chain, no subtraction.
+  static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word np) {
+    const Word q = mulhi(y, ws);
+    return y * w + q * np;
+  }
 };
 
 template <> struct Arith<32> {
@@ -35,11 +38,16 @@ template <> struct Arith<32> {
   static constexpr int WORD_BITS = 32;
   static __device__ __forceinline__ Word tw_w(const TW &t) { return t.x; }
   static __device__ __forceinline__ Word tw_ws(const TW &t) { return t.y; }
-  static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word p) {
-    Word q = __umulhi(y, ws);
-    return y * w - q * p;
+  // hi32(a*b) through IMAD.WIDE (4 pipe cycles) instead of the IMAD.HI (~6) that __umulhi compiles to
+  static __device__ __forceinline__ Word mulhi(Word a, Word b) {
+    Word hi;
+    asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.u32 t, %1, %2;\n\tmov.b64 {lo, %0}, t;\n\t}" : "=r"(hi) : "r"(a), "r"(b));
+    return hi;
   }
-  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umulhi(a, b); }
+  static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word np) {
+    const Word q = mulhi(y, ws);
+    return y * w + q * np;
+  }
 };
 
 template <> struct Arith<16> {
@@ -50,15 +58,28 @@ template <> struct Arith<16> {
   static __device__ __forceinline__ Word tw_w(const TW &t) { return t.x; }
   static __device__ __forceinline__ Word tw_ws(const TW &t) { return t.y; }
   // y < 2^16 (lazy values stay below 4p < 2^16), ws < 2^16: the products are exact in 32 bits
-  static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word p) {
-    Word q = (y * ws) >> 16;
-    return y * w - q * p;
+  static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word np) {
+    const Word q = (y * ws) >> 16;
+    return y * w + q * np;  // np = -p mod 2^32; the true value y*w - q*p < 2p < 2^15 survives the wrap
   }
   static __device__ __forceinline__ Word mulhi(Word a, Word b) { return (a * b) >> 16; }
 };
 
 // x - (x >= m ? m : 0)
 template <class W> static __device__ __forceinline__ W csub(W x, W m) { return x >= m ? x - m : x; }
+// Same, for the lazy-range reductions where m <= 2^(w-1) and x < 2m: the sign of x - m decides, which costs one
+// compare on the high word instead of a two-instruction 64-bit unsigned compare.
+static __device__ __forceinline__ uint64_t csub_lazy(uint64_t x, uint64_t m) {
+  const int64_t t = (int64_t)(x - m);
+  return t < 0 ? x : (uint64_t)t;
+}
+static __device__ __forceinline__ uint32_t csub_lazy(uint32_t x, uint32_t m) {
+  const int32_t t = (int32_t)(x - m);
+  return t < 0 ? x : (uint32_t)t;
+}
+// -p mod 2^w, hidden from constant propagation so products with it are not rewritten back into subtractions
+static __device__ __forceinline__ uint64_t opaque_neg(uint64_t p) { uint64_t n = (uint64_t)0 - p; asm("" : "+l"(n)); return n; }
+static __device__ __forceinline__ uint32_t opaque_neg(uint32_t p) { uint32_t n = (uint32_t)0 - p; asm("" : "+r"(n)); return n; }
 
 }  // namespace nflgpu
 #endif

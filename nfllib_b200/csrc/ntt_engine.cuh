@@ -51,16 +51,18 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int PADW = VEC;                      // 16 bytes of padding per row of E words
   static constexpr int ROW = E + PADW;
   static constexpr int TILE_WORDS = (NP > 1) ? (N >> e) * ROW : 0;
-#ifndef NFLGPU_TARGET_THREADS
-#define NFLGPU_TARGET_THREADS 256
-#endif
+  // CTA size: 256 threads (2+ CTAs per SM); 512 for N = 1024 x 64-bit (8 two-warp units per CTA, measured best)
+#ifdef NFLGPU_TARGET_THREADS
   static constexpr int TARGET_THREADS = NFLGPU_TARGET_THREADS;
+#else
+  static constexpr int TARGET_THREADS = (LB == 64 && LOGN == 10) ? 512 : 256;
+#endif
   static constexpr int SLOTS = (TPU >= TARGET_THREADS) ? 1 : TARGET_THREADS / TPU;
   static constexpr int THREADS = TPU * SLOTS;
 #ifdef NFLGPU_MIN_BLOCKS
   static constexpr int MIN_BLOCKS = NFLGPU_MIN_BLOCKS;
 #else
-  static constexpr int MIN_BLOCKS = (THREADS <= 256) ? 2 : 1;
+  static constexpr int MIN_BLOCKS = (LB == 64 && LOGN == 10) ? 2 : (THREADS <= 256) ? ((WB == 32 && E <= 32) ? 4 : 2) : 1;
 #endif
   static constexpr bool TW_SMEM = (size_t)N * sizeof(TW) <= 32768;
   static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)N * sizeof(TW) : 0;
@@ -115,7 +117,7 @@ template <class C> __device__ __forceinline__ void unit_sync(int slot, int lane_
 // Forward pass PASS: stages s0 .. s0+r-1, Cooley-Tukey, values lazily kept in [0, 4p).
 // tw points at this pass's entry [0][g]; consecutive e_idx are G entries apart.
 template <class C, int PASS> __device__ __forceinline__ void fwd_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
-                                                                      typename C::Word p, typename C::Word twop) {
+                                                                      typename C::Word np, typename C::Word twop) {
   typedef typename C::A A;
   typedef typename C::Word Word;
   constexpr int r = plan_r(C::n, C::WB, PASS), G = 1 << plan_s0(C::n, C::WB, PASS), e = C::e;
@@ -128,8 +130,8 @@ template <class C, int PASS> __device__ __forceinline__ void fwd_pass(typename C
       const int eidx = (1 << q) - 1 + (k >> (e - q));
       const typename C::TW t = tw[eidx * G];
       Word X = x[k];
-      if (!(PASS == 0 && q == 0)) X = csub(X, twop);  // first stage sees canonical input
-      const Word T = A::mul_shoup_lazy(x[k | (1 << bit)], A::tw_w(t), A::tw_ws(t), p);
+      if (!(PASS == 0 && q == 0)) X = csub_lazy(X, twop);  // first stage sees canonical input
+      const Word T = A::mul_shoup_lazy(x[k | (1 << bit)], A::tw_w(t), A::tw_ws(t), np);
       x[k] = X + T;
       x[k | (1 << bit)] = X - T + twop;
     }
@@ -139,7 +141,7 @@ template <class C, int PASS> __device__ __forceinline__ void fwd_pass(typename C
 // Inverse pass PASS: stages s0+r-1 .. s0 (reverse order), Gentleman-Sande, values lazily kept in [0, 2p);
 // the very last stage (PASS 0, q 0) also multiplies by N^-1 and produces canonical values.
 template <class C, int PASS> __device__ __forceinline__ void inv_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
-                                                                      typename C::Word p, typename C::Word twop,
+                                                                      typename C::Word p, typename C::Word np, typename C::Word twop,
                                                                       const typename C::TW ninv) {
   typedef typename C::A A;
   typedef typename C::Word Word;
@@ -153,12 +155,12 @@ template <class C, int PASS> __device__ __forceinline__ void inv_pass(typename C
       const int eidx = (1 << q) - 1 + (k >> (e - q));
       const typename C::TW t = tw[eidx * G];
       const Word U = x[k], V = x[k | (1 << bit)];
-      const Word D = A::mul_shoup_lazy(U - V + twop, A::tw_w(t), A::tw_ws(t), p);
+      const Word D = A::mul_shoup_lazy(U - V + twop, A::tw_w(t), A::tw_ws(t), np);
       if (PASS == 0 && q == 0) {
-        x[k] = csub(A::mul_shoup_lazy(U + V, A::tw_w(ninv), A::tw_ws(ninv), p), p);
-        x[k | (1 << bit)] = csub(D, p);
+        x[k] = csub_lazy(A::mul_shoup_lazy(U + V, A::tw_w(ninv), A::tw_ws(ninv), np), p);
+        x[k | (1 << bit)] = csub_lazy(D, p);
       } else {
-        x[k] = csub(U + V, twop);
+        x[k] = csub_lazy(U + V, twop);
         x[k | (1 << bit)] = D;
       }
     }
@@ -260,38 +262,39 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
 // forward: passes 1 .. NP-1 after pass 0 has stored its result into the tile
 template <class C, int PASS> struct FwdChain {
   static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
-                                             typename C::Word p, typename C::Word twop, int tid, int slot, int lane_base) {
+                                             typename C::Word p, typename C::Word np, typename C::Word twop, int tid, int slot,
+                                             int lane_base) {
     unit_sync<C>(slot, lane_base);
     tile_load<C, PASS>(x, tile, tid);
-    fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, twop);
+    fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
     if (PASS == C::NP - 1) {
 #pragma unroll
-      for (int k = 0; k < C::E; ++k) x[k] = csub(csub(x[k], twop), p);  // [0,4p) -> canonical (core.hpp:523-529)
+      for (int k = 0; k < C::E; ++k) x[k] = csub_lazy(csub_lazy(x[k], twop), p);  // [0,4p) -> canonical (core.hpp:523-529)
     }
     tile_store<C, PASS>(x, tile, tid);
-    FwdChain<C, PASS + 1>::run(x, tile, tw, p, twop, tid, slot, lane_base);
+    FwdChain<C, PASS + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
   }
 };
 template <class C> struct FwdChain<C, C::NP> {
   static __device__ __forceinline__ void run(typename C::Word (&)[C::E], typename C::Word *, const typename C::TW *, typename C::Word,
-                                             typename C::Word, int, int, int) {}
+                                             typename C::Word, typename C::Word, int, int, int) {}
 };
 
 // inverse: passes NP-1 .. 1 (tile -> registers -> tile); pass 0 is done by the kernel body
 template <class C, int PASS> struct InvChain {
   static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
-                                             typename C::Word p, typename C::Word twop, const typename C::TW ninv, int tid, int slot,
-                                             int lane_base) {
+                                             typename C::Word p, typename C::Word np, typename C::Word twop, const typename C::TW ninv,
+                                             int tid, int slot, int lane_base) {
     unit_sync<C>(slot, lane_base);
     tile_load<C, PASS>(x, tile, tid);
-    inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, twop, ninv);
+    inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, np, twop, ninv);
     tile_store<C, PASS>(x, tile, tid);
-    InvChain<C, PASS - 1>::run(x, tile, tw, p, twop, ninv, tid, slot, lane_base);
+    InvChain<C, PASS - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
   }
 };
 template <class C> struct InvChain<C, 0> {
   static __device__ __forceinline__ void run(typename C::Word (&)[C::E], typename C::Word *, const typename C::TW *, typename C::Word,
-                                             typename C::Word, const typename C::TW, int, int, int) {}
+                                             typename C::Word, typename C::Word, const typename C::TW, int, int, int) {}
 };
 
 // ---- kernels -------------------------------------------------------------------------------------------------
@@ -324,7 +327,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   extern __shared__ __align__(128) unsigned char smem[];
   const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const TW *tw = stage_twiddles<C>(a, cm, smem);
-  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p;
+  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   const int slot = threadIdx.x / C::TPU, tid = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tid & 31);
   Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
@@ -337,14 +340,14 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     // pass 0 reads straight from global memory: for fixed k the unit's threads touch consecutive limbs
 #pragma unroll
     for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, 0>(tid, k));
-    fwd_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), p, twop);
+    fwd_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), np, twop);
     if (C::NP == 1) {
 #pragma unroll
-      for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)csub(csub(x[k], twop), p);
+      for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)csub_lazy(csub_lazy(x[k], twop), p);
     } else {
       unit_sync<C>(slot, lane_base);  // previous unit's copy-out has finished reading the tile
       tile_store<C, 0>(x, tile, tid);
-      FwdChain<C, 1>::run(x, tile, tw, p, twop, tid, slot, lane_base);
+      FwdChain<C, 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
       tile_to_gmem<C>(tile, dst + ubase, tid);
     }
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const TW *tw = stage_twiddles<C>(a, cm, smem);
   const TW ninv = tw[C::N - 1];
-  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p;
+  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   const int slot = threadIdx.x / C::TPU, tid = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tid & 31);
   Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
@@ -377,11 +380,11 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     } else {
       unit_sync<C>(slot, lane_base);  // previous unit's pass 0 has finished reading the tile
       gmem_to_tile<C>(tile, src + ubase, tid);
-      InvChain<C, C::NP - 1>::run(x, tile, tw, p, twop, ninv, tid, slot, lane_base);
+      InvChain<C, C::NP - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
       tile_load<C, 0>(x, tile, tid);
     }
-    inv_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), p, twop, ninv);
+    inv_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), p, np, twop, ninv);
     // pass 0 writes straight to global memory (lane-contiguous for fixed k)
 #pragma unroll
     for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)x[k];

@@ -26,16 +26,20 @@
 
 namespace nflgpu {
 
-// Largest radix exponent per thread: 32 coefficients of 64 bits or 64 of 32 bits = 64 data registers.
-// (NFLGPU_EMAX64 / NFLGPU_EMAX32 are tuning overrides used by tools/variants.sh experiments.)
-#ifndef NFLGPU_EMAX64
-#define NFLGPU_EMAX64 5
+// Largest radix exponent per thread.  64-bit words: 32 coefficients = 64 data registers (16 for N = 1024, where the
+// smaller register footprint doubles the resident warps and measured 10 % faster, profiles/r01b_*); 32-bit words: 64
+// coefficients up to N = 2048, 32 above (the shapes (2,5,5) .. (5,5,5) beat (6,6) / (1,6,6) on the N = 4096 config).
+// NFLGPU_EMAX64 / NFLGPU_EMAX32 override the table (tools/variants.sh experiments).
+NFLGPU_HD constexpr int plan_emax(int n, int word_bits) {
+#ifdef NFLGPU_EMAX64
+  if (word_bits == 64) return NFLGPU_EMAX64;
 #endif
-#ifndef NFLGPU_EMAX32
-#define NFLGPU_EMAX32 6
+#ifdef NFLGPU_EMAX32
+  if (word_bits != 64) return NFLGPU_EMAX32;
 #endif
-NFLGPU_HD constexpr int plan_emax(int word_bits) { return word_bits == 64 ? NFLGPU_EMAX64 : NFLGPU_EMAX32; }
-NFLGPU_HD constexpr int plan_npass(int n, int word_bits) { return (n + plan_emax(word_bits) - 1) / plan_emax(word_bits); }
+  return word_bits == 64 ? (n == 10 ? 4 : 5) : (n >= 12 ? 5 : 6);
+}
+NFLGPU_HD constexpr int plan_npass(int n, int word_bits) { return (n + plan_emax(n, word_bits) - 1) / plan_emax(n, word_bits); }
 NFLGPU_HD constexpr int plan_e(int n, int word_bits) { return (n + plan_npass(n, word_bits) - 1) / plan_npass(n, word_bits); }
 // stages in pass i (only the first pass may be short)
 NFLGPU_HD constexpr int plan_r(int n, int word_bits, int i) {

@@ -8,7 +8,7 @@ from oracle_lib import Oracle, golden_params, random_polys
 
 
 def plan(n, wb):
-    emax = 5 if wb == 64 else 6
+    emax = (4 if n == 10 else 5) if wb == 64 else (5 if n >= 12 else 6)  # mirrors plan_emax() in ntt_plan.h
     npass = (n + emax - 1) // emax
     e = (n + npass - 1) // npass
     r = [n - e * (npass - 1)] + [e] * (npass - 1)
