@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -17,13 +18,14 @@ namespace nflgpu {
 static thread_local std::string g_last_error;
 void set_error(const std::string &msg) { g_last_error = msg; }
 
-cudaError_t launch_ntt(int limb_bits, int log2_degree, bool inverse, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
-  switch (limb_bits) {
-    case 64: return inverse ? launch_ntt_u64_inv(log2_degree, l, device, num_sms, stream) : launch_ntt_u64_fwd(log2_degree, l, device, num_sms, stream);
-    case 32: return inverse ? launch_ntt_u32_inv(log2_degree, l, device, num_sms, stream) : launch_ntt_u32_fwd(log2_degree, l, device, num_sms, stream);
-    case 16: return inverse ? launch_ntt_u16_inv(log2_degree, l, device, num_sms, stream) : launch_ntt_u16_fwd(log2_degree, l, device, num_sms, stream);
-  }
-  return cudaErrorInvalidValue;
+cudaError_t launch_ntt(int limb_bits, int log2_degree, int mode, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
+  typedef cudaError_t (*fn_t)(int, const NttLaunch &, int, int, cudaStream_t);
+  static const fn_t table[3][3] = {{launch_ntt_u16_fwd, launch_ntt_u16_inv, launch_ntt_u16_fwdmul},
+                                   {launch_ntt_u32_fwd, launch_ntt_u32_inv, launch_ntt_u32_fwdmul},
+                                   {launch_ntt_u64_fwd, launch_ntt_u64_inv, launch_ntt_u64_fwdmul}};
+  const int li = limb_bits == 16 ? 0 : limb_bits == 32 ? 1 : limb_bits == 64 ? 2 : -1;
+  if (li < 0 || mode < 0 || mode > 2) return cudaErrorInvalidValue;
+  return table[li][mode](log2_degree, l, device, num_sms, stream);
 }
 
 bool ntt_supported(int limb_bits, int n) {
@@ -65,7 +67,8 @@ struct nflgpu_ctx {
   uint64_t *d_consts = nullptr;     // Barrett constants, pointwise.h
   void *d_tw_fwd = nullptr, *d_tw_inv = nullptr;
   std::atomic<uint64_t> launches{0};
-  HostStage stage[3];
+  static constexpr int kStages = 4;
+  HostStage stage[kStages];
   size_t stage_polys = 0;
 };
 
@@ -88,17 +91,19 @@ int check_buf(const nflgpu_ctx *ctx, const void *p, const char *name) {
   return NFLGPU_OK;
 }
 
-int run_ntt(nflgpu_ctx *ctx, bool inverse, void *dst, const void *src, size_t batch, void *stream) {
+int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch, void *stream, const void *other = nullptr) {
   int rc;
   if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, src, "src"))) return rc;
+  if (mode == 2 && (rc = check_buf(ctx, other, "other"))) return rc;
   if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
   if (batch == 0) return NFLGPU_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
   NttLaunch l;
-  l.src = src; l.dst = dst; l.tw = inverse ? ctx->d_tw_inv : ctx->d_tw_fwd; l.moduli = ctx->d_moduli_word;
+  l.src = src; l.dst = dst; l.tw = mode == 1 ? ctx->d_tw_inv : ctx->d_tw_fwd; l.moduli = ctx->d_moduli_word;
   l.nmoduli = (uint32_t)ctx->nmoduli; l.batch = (uint32_t)batch;
-  CUDA_TRY(launch_ntt(ctx->limb_bits, ctx->log2_degree, inverse, l, ctx->device, ctx->num_sms, (cudaStream_t)stream));
+  l.other = other; l.consts = ctx->d_consts;
+  CUDA_TRY(launch_ntt(ctx->limb_bits, ctx->log2_degree, mode, l, ctx->device, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return NFLGPU_OK;
 }
@@ -321,8 +326,8 @@ int nflgpu_sync(nflgpu_ctx *ctx, void *stream) {
   return NFLGPU_OK;
 }
 
-int nflgpu_ntt_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, false, dst, src, batch, stream); }
-int nflgpu_ntt_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, true, dst, src, batch, stream); }
+int nflgpu_ntt_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, 0, dst, src, batch, stream); }
+int nflgpu_ntt_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, 1, dst, src, batch, stream); }
 
 int nflgpu_mul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
   return run_pw(ctx, PW_MUL, 2, dst, a, b, nullptr, nullptr, batch, stream);
@@ -356,9 +361,9 @@ int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, siz
   void *tmp = nullptr;
   const size_t bytes = nflgpu_batch_bytes(ctx, batch);
   CUDA_TRY(cudaMallocAsync(&tmp, bytes, s));
-  // fwd(a) -> dst, fwd(b) -> tmp, dst = dst * tmp, dst = inv(dst)
-  if ((rc = run_ntt(ctx, false, dst, a, batch, stream)) || (rc = run_ntt(ctx, false, tmp, b, batch, stream)) ||
-      (rc = run_pw(ctx, PW_MUL, 2, dst, dst, tmp, nullptr, nullptr, batch, stream)) || (rc = run_ntt(ctx, true, dst, dst, batch, stream))) {
+  // three launches: tmp = ntt(a);  dst = ntt(b) * tmp (product fused into the forward kernel's copy-out);  dst = intt(dst)
+  if ((rc = run_ntt(ctx, 0, tmp, a, batch, stream)) || (rc = run_ntt(ctx, 2, dst, b, batch, stream, tmp)) ||
+      (rc = run_ntt(ctx, 1, dst, dst, batch, stream))) {
     cudaFreeAsync(tmp, s);
     return rc;
   }
@@ -390,11 +395,17 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
 
   const size_t poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
-  // chunk: ~32 MiB per operand, at least one polynomial; three stages in flight (H2D / kernel / D2H overlap)
-  size_t chunk = (32u << 20) / poly_bytes;
+  // chunk: ~8 MiB per operand (small enough that pipeline fill/drain is ~6 % of a 128 MiB batch, large enough
+  // to keep PCIe DMA efficient), at least one polynomial; kStages chunks in flight (H2D / kernel / D2H overlap)
+  size_t chunk_bytes = 8u << 20;
+  if (const char *env = std::getenv("NFLGPU_HOST_CHUNK_MIB")) {  // tuning knob
+    const long v = std::atol(env);
+    if (v > 0 && v <= 1024) chunk_bytes = (size_t)v << 20;
+  }
+  size_t chunk = chunk_bytes / poly_bytes;
   if (chunk == 0) chunk = 1;
   if (chunk > batch) chunk = batch;
-  if (ctx->stage_polys < chunk) {
+  if (ctx->stage_polys != chunk) {
     for (auto &s : ctx->stage) {
       if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       for (int i = 0; i < 4; ++i) {
@@ -406,12 +417,14 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
     ctx->stage_polys = chunk;
   }
   bool pinned[4] = {is_pinned(a_host), nin >= 2 && is_pinned(b_host), nin >= 3 && is_pinned(c_host), is_pinned(dst_host)};
-  struct Pending { size_t first, count; bool active; } pend[3] = {{0, 0, false}, {0, 0, false}, {0, 0, false}};
+  constexpr int NS = nflgpu_ctx::kStages;
+  struct Pending { size_t first, count; bool active; } pend[NS] = {};
   int rc = NFLGPU_OK;
   size_t done = 0;
-  for (int k = 0; done < batch || pend[0].active || pend[1].active || pend[2].active; k = (k + 1) % 3) {
+  auto any_pending = [&]() { for (int i = 0; i < NS; ++i) if (pend[i].active) return true; return false; };
+  for (int k = 0; done < batch || any_pending(); k = (k + 1) % NS) {
     HostStage &s = ctx->stage[k];
-    if (pend[k].active) {  // retire the chunk that used this stage three steps ago
+    if (pend[k].active) {  // retire the chunk that used this stage kStages steps ago
       CUDA_TRY(cudaStreamSynchronize(s.stream));
       if (!pinned[3]) std::memcpy(static_cast<char *>(dst_host) + pend[k].first * poly_bytes, s.pin[3], pend[k].count * poly_bytes);
       pend[k].active = false;

@@ -12,10 +12,13 @@ struct NttLaunch {
   const void *tw;      // device TW[nmoduli][N] of the requested direction
   const void *moduli;  // device Word[nmoduli]
   uint32_t nmoduli, batch;
+  const void *other = nullptr;        // fused epilogue operand (mode 2 only)
+  const uint64_t *consts = nullptr;   // Barrett constants (mode 2 only)
 };
 
 // Returns cudaErrorInvalidValue when (limb_bits, log2_degree) has no kernel.
-cudaError_t launch_ntt(int limb_bits, int log2_degree, bool inverse, const NttLaunch &l, int device, int num_sms,
+// mode: 0 forward, 1 inverse, 2 forward fused with "* other"
+cudaError_t launch_ntt(int limb_bits, int log2_degree, int mode, const NttLaunch &l, int device, int num_sms,
                        cudaStream_t stream);
 bool ntt_supported(int limb_bits, int log2_degree);
 
@@ -24,6 +27,7 @@ bool ntt_supported(int limb_bits, int log2_degree);
 NFLGPU_DECL_LAUNCHER(launch_ntt_u64_fwd) NFLGPU_DECL_LAUNCHER(launch_ntt_u64_inv)
 NFLGPU_DECL_LAUNCHER(launch_ntt_u32_fwd) NFLGPU_DECL_LAUNCHER(launch_ntt_u32_inv)
 NFLGPU_DECL_LAUNCHER(launch_ntt_u16_fwd) NFLGPU_DECL_LAUNCHER(launch_ntt_u16_inv)
+NFLGPU_DECL_LAUNCHER(launch_ntt_u64_fwdmul) NFLGPU_DECL_LAUNCHER(launch_ntt_u32_fwdmul) NFLGPU_DECL_LAUNCHER(launch_ntt_u16_fwdmul)
 
 }  // namespace nflgpu
 #endif

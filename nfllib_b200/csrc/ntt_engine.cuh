@@ -21,6 +21,7 @@
 #define NFLGPU_NTT_ENGINE_CUH
 
 #include "modarith.cuh"
+#include "modmul.cuh"
 #include "ntt_plan.h"
 
 namespace nflgpu {
@@ -33,6 +34,9 @@ struct NttArgs {
   uint32_t nmoduli;
   uint32_t batch;
   uint32_t ctas_per_residue;
+  // fused epilogue of the forward kernel (nflgpu_polymul): dst = ntt_pow_phi(src) * other, coefficient-wise
+  const void *other;       // Store[batch][nmoduli][N], canonical, NTT domain; null when unused
+  const uint64_t *consts;  // Barrett constants per residue (pointwise.h)
 };
 
 template <int LB, int LOGN> struct NttCfg {
@@ -237,6 +241,38 @@ template <class C> __device__ __forceinline__ void tile_to_gmem(const typename C
     }
   }
 }
+// copy-out with the coefficient-wise product fused in: g[pos] = tile[pos] * other[pos] mod p  (ops.hpp:184-219)
+template <class C, int LB> __device__ __forceinline__ void tile_to_gmem_mul(const typename C::Word *tile, typename C::Store *g,
+                                                                            const typename C::Store *other, int tid, typename C::Word p,
+                                                                            uint64_t k) {
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  constexpr int CHUNKS = C::N / C::VEC;
+#pragma unroll
+  for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
+    const int ch = tid + j * C::TPU;
+    if (CHUNKS % C::TPU != 0 && ch >= CHUNKS) break;
+    const int pos = ch * C::VEC;
+    uint4 t = *reinterpret_cast<const uint4 *>(tile + C::pad(pos));
+    Word *w = reinterpret_cast<Word *>(&t);
+    if (sizeof(Store) == sizeof(Word)) {
+      const uint4 o = __ldg(reinterpret_cast<const uint4 *>(other + pos));
+      const Word *ow = reinterpret_cast<const Word *>(&o);
+#pragma unroll
+      for (int i = 0; i < C::VEC; ++i) w[i] = PW<LB>::mulmod(w[i], ow[i], p, k);
+      *reinterpret_cast<uint4 *>(g + pos) = t;
+    } else {
+      const uint2 o = __ldg(reinterpret_cast<const uint2 *>(other + pos));
+      const Word ow[4] = {o.x & 0xffffu, o.x >> 16, o.y & 0xffffu, o.y >> 16};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] = PW<LB>::mulmod(w[i], ow[i], p, k);
+      uint2 r;
+      r.x = (uint32_t)w[0] | ((uint32_t)w[1] << 16);
+      r.y = (uint32_t)w[2] | ((uint32_t)w[3] << 16);
+      *reinterpret_cast<uint2 *>(g + pos) = r;
+    }
+  }
+}
 template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word *tile, const typename C::Store *g, int tid) {
   typedef typename C::Word Word;
   typedef typename C::Store Store;
@@ -318,7 +354,7 @@ template <class C> __device__ __forceinline__ const typename C::TW *stage_twiddl
   return tws;
 }
 
-template <int LB, int LOGN>
+template <int LB, int LOGN, bool MUL>
 __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::MIN_BLOCKS) ntt_fwd_kernel(const NttArgs a) {
   typedef NttCfg<LB, LOGN> C;
   typedef typename C::Word Word;
@@ -343,13 +379,18 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     fwd_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), np, twop);
     if (C::NP == 1) {
 #pragma unroll
-      for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)csub_lazy(csub_lazy(x[k], twop), p);
+      for (int k = 0; k < C::E; ++k) {
+        Word v = csub_lazy(csub_lazy(x[k], twop), p);
+        if (MUL) v = PW<LB>::mulmod(v, (Word)__ldg(reinterpret_cast<const Store *>(a.other) + ubase + pass_pos<C, 0>(tid, k)), p, a.consts[cm]);
+        dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)v;
+      }
     } else {
       unit_sync<C>(slot, lane_base);  // previous unit's copy-out has finished reading the tile
       tile_store<C, 0>(x, tile, tid);
       FwdChain<C, 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
-      tile_to_gmem<C>(tile, dst + ubase, tid);
+      if (MUL) tile_to_gmem_mul<C, LB>(tile, dst + ubase, reinterpret_cast<const Store *>(a.other) + ubase, tid, p, a.consts[cm]);
+      else tile_to_gmem<C>(tile, dst + ubase, tid);
     }
   }
 }

@@ -6,11 +6,13 @@
 
 namespace nflgpu {
 
-template <int LB, int LOGN, bool INV> cudaError_t launch_ntt_one(const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
+// MODE: 0 forward, 1 inverse, 2 forward with the fused "* other" epilogue
+template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
   typedef NttCfg<LB, LOGN> C;
   void (*kernel)(const NttArgs);
-  if constexpr (INV) kernel = ntt_inv_kernel<LB, LOGN>;
-  else kernel = ntt_fwd_kernel<LB, LOGN>;
+  if constexpr (MODE == 1) kernel = ntt_inv_kernel<LB, LOGN>;
+  else if constexpr (MODE == 2) kernel = ntt_fwd_kernel<LB, LOGN, true>;
+  else kernel = ntt_fwd_kernel<LB, LOGN, false>;
   // per-device one-time setup: opt in to the shared-memory size and ask the occupancy calculator
   static int blocks_per_sm[64] = {0};
   if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
@@ -32,6 +34,7 @@ template <int LB, int LOGN, bool INV> cudaError_t launch_ntt_one(const NttLaunch
   NttArgs a;
   a.src = l.src; a.dst = l.dst; a.tw = l.tw; a.moduli = l.moduli;
   a.nmoduli = l.nmoduli; a.batch = l.batch; a.ctas_per_residue = cpr;
+  a.other = l.other; a.consts = l.consts;
   kernel<<<cpr * l.nmoduli, C::THREADS, C::SMEM_BYTES, stream>>>(a);
   return cudaGetLastError();
 }
@@ -40,11 +43,11 @@ template <int LB, int LOGN, bool INV> cudaError_t launch_ntt_one(const NttLaunch
 
 // NFLGPU_ONLY_LOGN restricts the instantiations to one size (fast experiment builds, tools/variants.sh)
 #ifdef NFLGPU_ONLY_LOGN
-#define NFLGPU_NTT_CASE(LB, LOGN, INV) \
-  case LOGN: if constexpr (LOGN == NFLGPU_ONLY_LOGN) return launch_ntt_one<LB, LOGN, INV>(l, device, num_sms, stream); else break;
+#define NFLGPU_NTT_CASE(LB, LOGN, MODE) \
+  case LOGN: if constexpr (LOGN == NFLGPU_ONLY_LOGN) return launch_ntt_one<LB, LOGN, MODE>(l, device, num_sms, stream); else break;
 #else
-#define NFLGPU_NTT_CASE(LB, LOGN, INV) \
-  case LOGN: return launch_ntt_one<LB, LOGN, INV>(l, device, num_sms, stream);
+#define NFLGPU_NTT_CASE(LB, LOGN, MODE) \
+  case LOGN: return launch_ntt_one<LB, LOGN, MODE>(l, device, num_sms, stream);
 #endif
 
 #endif

@@ -3,8 +3,8 @@
 namespace nflgpu {
 cudaError_t launch_ntt_u16_fwd(int log2_degree, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
   switch (log2_degree) {
-    NFLGPU_NTT_CASE(16, 4, false) NFLGPU_NTT_CASE(16, 5, false) NFLGPU_NTT_CASE(16, 6, false) NFLGPU_NTT_CASE(16, 7, false)
-    NFLGPU_NTT_CASE(16, 8, false) NFLGPU_NTT_CASE(16, 9, false)
+    NFLGPU_NTT_CASE(16, 4, 0) NFLGPU_NTT_CASE(16, 5, 0) NFLGPU_NTT_CASE(16, 6, 0) NFLGPU_NTT_CASE(16, 7, 0)
+    NFLGPU_NTT_CASE(16, 8, 0) NFLGPU_NTT_CASE(16, 9, 0)
   }
   return cudaErrorInvalidValue;
 }

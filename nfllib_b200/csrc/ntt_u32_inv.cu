@@ -3,10 +3,10 @@
 namespace nflgpu {
 cudaError_t launch_ntt_u32_inv(int log2_degree, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
   switch (log2_degree) {
-    NFLGPU_NTT_CASE(32, 3, true) NFLGPU_NTT_CASE(32, 4, true) NFLGPU_NTT_CASE(32, 5, true) NFLGPU_NTT_CASE(32, 6, true)
-    NFLGPU_NTT_CASE(32, 7, true) NFLGPU_NTT_CASE(32, 8, true) NFLGPU_NTT_CASE(32, 9, true) NFLGPU_NTT_CASE(32, 10, true)
-    NFLGPU_NTT_CASE(32, 11, true) NFLGPU_NTT_CASE(32, 12, true) NFLGPU_NTT_CASE(32, 13, true) NFLGPU_NTT_CASE(32, 14, true)
-    NFLGPU_NTT_CASE(32, 15, true)
+    NFLGPU_NTT_CASE(32, 3, 1) NFLGPU_NTT_CASE(32, 4, 1) NFLGPU_NTT_CASE(32, 5, 1) NFLGPU_NTT_CASE(32, 6, 1)
+    NFLGPU_NTT_CASE(32, 7, 1) NFLGPU_NTT_CASE(32, 8, 1) NFLGPU_NTT_CASE(32, 9, 1) NFLGPU_NTT_CASE(32, 10, 1)
+    NFLGPU_NTT_CASE(32, 11, 1) NFLGPU_NTT_CASE(32, 12, 1) NFLGPU_NTT_CASE(32, 13, 1) NFLGPU_NTT_CASE(32, 14, 1)
+    NFLGPU_NTT_CASE(32, 15, 1)
   }
   return cudaErrorInvalidValue;
 }

@@ -3,10 +3,10 @@
 namespace nflgpu {
 cudaError_t launch_ntt_u64_fwd(int log2_degree, const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
   switch (log2_degree) {
-    NFLGPU_NTT_CASE(64, 2, false) NFLGPU_NTT_CASE(64, 3, false) NFLGPU_NTT_CASE(64, 4, false) NFLGPU_NTT_CASE(64, 5, false)
-    NFLGPU_NTT_CASE(64, 6, false) NFLGPU_NTT_CASE(64, 7, false) NFLGPU_NTT_CASE(64, 8, false) NFLGPU_NTT_CASE(64, 9, false)
-    NFLGPU_NTT_CASE(64, 10, false) NFLGPU_NTT_CASE(64, 11, false) NFLGPU_NTT_CASE(64, 12, false) NFLGPU_NTT_CASE(64, 13, false)
-    NFLGPU_NTT_CASE(64, 14, false)
+    NFLGPU_NTT_CASE(64, 2, 0) NFLGPU_NTT_CASE(64, 3, 0) NFLGPU_NTT_CASE(64, 4, 0) NFLGPU_NTT_CASE(64, 5, 0)
+    NFLGPU_NTT_CASE(64, 6, 0) NFLGPU_NTT_CASE(64, 7, 0) NFLGPU_NTT_CASE(64, 8, 0) NFLGPU_NTT_CASE(64, 9, 0)
+    NFLGPU_NTT_CASE(64, 10, 0) NFLGPU_NTT_CASE(64, 11, 0) NFLGPU_NTT_CASE(64, 12, 0) NFLGPU_NTT_CASE(64, 13, 0)
+    NFLGPU_NTT_CASE(64, 14, 0)
   }
   return cudaErrorInvalidValue;
 }

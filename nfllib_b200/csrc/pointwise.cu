@@ -8,68 +8,9 @@
 // integer division is needed to find it.  Results are canonical and bit-identical to the reference's.
 #include "pointwise.h"
 #include "modarith.cuh"
+#include "modmul.cuh"
 
 namespace nflgpu {
-
-// ---- per-limb exact modular multiply (any correct x*y mod p is bit-identical) -----------
-
-template <int LB> struct PW;
-
-template <> struct PW<64> {
-  typedef uint64_t Word;
-  typedef uint64_t Store;
-  static constexpr int VEC = 2;
-  // ops.hpp:201-219: res = x*y (128 bit); q = Pn*hi(res) + (res << 2); r = lo(res) - hi(q)*p; r -= p if r >= p.
-  // (2^128 / p = 4*2^64 + Pn for NFLlib's 62-bit moduli.)
-  static __device__ __forceinline__ Word mulmod(Word x, Word y, Word p, uint64_t pn) {
-    const Word lo = x * y, hi = __umul64hi(x, y);
-    const Word a_lo = pn * hi, a_hi = __umul64hi(pn, hi);
-    const Word b_lo = lo << 2, b_hi = (hi << 2) | (lo >> 62);
-    const Word s_lo = a_lo + b_lo;
-    const Word q_hi = a_hi + b_hi + (s_lo < a_lo ? 1 : 0);
-    Word r = lo - q_hi * p;
-    return csub(r, p);
-  }
-  // floor(x * 2^64 / p) for x < p:  estimate with mu = 4*2^64 + pn, then at most two corrections
-  static __device__ __forceinline__ Word shoup_of(Word x, Word p, uint64_t pn) {
-    Word q = (x << 2) + __umul64hi(x, pn);
-    Word rem = (Word)0 - q * p;  // x*2^64 - q*p, exact because it is < 3p < 2^64
-    if (rem >= p) { rem -= p; ++q; }
-    if (rem >= p) { rem -= p; ++q; }
-    return q;
-  }
-  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umul64hi(a, b); }
-};
-
-template <> struct PW<32> {
-  typedef uint32_t Word;
-  typedef uint32_t Store;
-  static constexpr int VEC = 4;
-  // (x*y) % p (ops.hpp:184-197) through Barrett with mu = floor(2^64 / p): q is exact or one short
-  static __device__ __forceinline__ Word mulmod(Word x, Word y, Word p, uint64_t mu) {
-    const uint64_t res = (uint64_t)x * y;
-    const uint64_t q = __umul64hi(res, mu);
-    Word r = (Word)res - (Word)q * p;
-    return csub(r, p);
-  }
-  static __device__ __forceinline__ Word shoup_of(Word x, Word p, uint64_t mu) {
-    const uint64_t num = (uint64_t)x << 32;
-    uint64_t q = __umul64hi(num, mu);
-    Word rem = (Word)0 - (Word)q * p;  // num - q*p < 2p
-    if (rem >= p) ++q;
-    return (Word)q;
-  }
-  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umulhi(a, b); }
-};
-
-template <> struct PW<16> {
-  typedef uint32_t Word;
-  typedef uint16_t Store;
-  static constexpr int VEC = 8;
-  static __device__ __forceinline__ Word mulmod(Word x, Word y, Word p, uint64_t) { return (x * y) % p; }
-  static __device__ __forceinline__ Word shoup_of(Word x, Word p, uint64_t) { return (x << 16) / p; }
-  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return (a * b) >> 16; }
-};
 
 // ---- functors ------------------------------------------------------------------------------------------------
 
