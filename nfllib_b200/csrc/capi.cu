@@ -395,9 +395,40 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
 
   const size_t poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
-  // chunk: ~8 MiB per operand (small enough that pipeline fill/drain is ~6 % of a 128 MiB batch, large enough
-  // to keep PCIe DMA efficient), at least one polynomial; kStages chunks in flight (H2D / kernel / D2H overlap)
-  size_t chunk_bytes = 8u << 20;
+
+  // Zero-copy path: when every operand lives in pinned (device-mapped, UVA) host memory the kernels read and write it
+  // directly over PCIe — no staging buffers, no pipeline fill/drain, copy and compute overlap at warp granularity.
+  // NFLGPU_HOST_ZEROCOPY=0 forces the staged pipeline below.
+  {
+    const char *zc = std::getenv("NFLGPU_HOST_ZEROCOPY");
+    bool all_pinned = is_pinned(dst_host);
+    for (int i = 0; i < nin; ++i) all_pinned = all_pinned && is_pinned(in[i]);
+    if (all_pinned && !(zc && zc[0] == '0')) {
+      void *dp[4] = {nullptr, nullptr, nullptr, nullptr};
+      const void *hp[4] = {a_host, b_host, c_host, dst_host};
+      for (int i = 0; i < 4; ++i)
+        if (hp[i]) CUDA_TRY(cudaHostGetDevicePointer(&dp[i], const_cast<void *>(hp[i]), 0));
+      if (!ctx->stage[0].stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stage[0].stream, cudaStreamNonBlocking));
+      void *st = ctx->stage[0].stream;
+      int rc = NFLGPU_OK;
+      switch (op) {
+        case 0: rc = nflgpu_ntt_fwd(ctx, dp[3], dp[0], batch, st); break;
+        case 1: rc = nflgpu_ntt_inv(ctx, dp[3], dp[0], batch, st); break;
+        case 2: rc = nflgpu_mul(ctx, dp[3], dp[0], dp[1], batch, st); break;
+        case 3: rc = nflgpu_mul_shoup(ctx, dp[3], dp[0], dp[1], dp[2], batch, st); break;
+        case 4: rc = nflgpu_compute_shoup(ctx, dp[3], dp[0], batch, st); break;
+        case 5: rc = nflgpu_add(ctx, dp[3], dp[0], dp[1], batch, st); break;
+        case 6: rc = nflgpu_sub(ctx, dp[3], dp[0], dp[1], batch, st); break;
+        case 8: rc = nflgpu_polymul(ctx, dp[3], dp[0], dp[1], batch, st); break;
+        case 9: rc = nflgpu_muladd(ctx, dp[3], dp[0], dp[1], dp[2], batch, st); break;
+      }
+      if (rc != NFLGPU_OK) return rc;
+      CUDA_TRY(cudaStreamSynchronize(ctx->stage[0].stream));
+      return NFLGPU_OK;
+    }
+  }
+  // chunk: ~16 MiB per operand (best of a 1..64 MiB sweep on B200 / PCIe gen5, tools/e2e_sweep.py), at least one polynomial; kStages chunks in flight (H2D / kernel / D2H overlap)
+  size_t chunk_bytes = 16u << 20;
   if (const char *env = std::getenv("NFLGPU_HOST_CHUNK_MIB")) {  // tuning knob
     const long v = std::atol(env);
     if (v > 0 && v <= 1024) chunk_bytes = (size_t)v << 20;
