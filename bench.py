@@ -321,7 +321,7 @@ def run_b200(args):
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
                "data": "synthetic", "config": config(world),
-               "roofline": {"bound": "hbm", "kernel": "ntt_fwd_kernel<64,10> (forward, one launch per batch)", "achieved": achieved,
+               "roofline": {"bound": "hbm", "kernel": "ntt_fwd_kernel<64,10,false> (forward, one launch per batch)", "achieved": achieved,
                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                             "algorithmic_bytes_per_launch": ALG_BYTES_PER_TRANSFORM * BATCH, "fwd_ms_per_launch": fwd_ms,
                             "inv_ms_per_launch": inv_ms,

@@ -396,14 +396,14 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
 
   const size_t poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
 
-  // Zero-copy path: when every operand lives in pinned (device-mapped, UVA) host memory the kernels read and write it
-  // directly over PCIe — no staging buffers, no pipeline fill/drain, copy and compute overlap at warp granularity.
-  // NFLGPU_HOST_ZEROCOPY=0 forces the staged pipeline below.
+  // Optional zero-copy path (NFLGPU_HOST_ZEROCOPY=1): when every operand lives in pinned (device-mapped, UVA) host
+  // memory the kernels read and write it directly over PCIe — no staging buffers.  Measured on B200 / PCIe gen5 it
+  // moves 37 GB/s each way against 41 GB/s for the staged pipeline below (tools/e2e_sweep.py), so it is off by default.
   {
     const char *zc = std::getenv("NFLGPU_HOST_ZEROCOPY");
     bool all_pinned = is_pinned(dst_host);
     for (int i = 0; i < nin; ++i) all_pinned = all_pinned && is_pinned(in[i]);
-    if (all_pinned && !(zc && zc[0] == '0')) {
+    if (all_pinned && zc && zc[0] == '1') {
       void *dp[4] = {nullptr, nullptr, nullptr, nullptr};
       const void *hp[4] = {a_host, b_host, c_host, dst_host};
       for (int i = 0; i < 4; ++i)
