@@ -48,7 +48,7 @@ typedef enum {
  * companions, N^-1.  Tables are derived from the moduli and the primitive 2*kMaxPolyDegree-th roots exactly
  * as core.hpp:640-665 derives phi and N^-1, then uploaded to `device`.
  *   limb_bits      16, 32 or 64  (params<uint16_t|uint32_t|uint64_t>, params.hpp:12,44,83)
- *   degree         power of two, 32 bytes <= degree*limb_bits/8, degree <= 32768 (16384 for 64-bit limbs)
+ *   degree         power of two, 32 bytes <= degree*limb_bits/8, degree <= params<T>::kMaxPolyDegree (512 / 32768 / 2^20)
  *   first_modulus  index of the first modulus in NFLlib's table; a context covers
  *                  P[first_modulus .. first_modulus+nmoduli) — nonzero when residues are sharded over GPUs
  *   moduli, roots  optional caller-provided tables of `nmoduli` uint64_t each (params<T>::P and

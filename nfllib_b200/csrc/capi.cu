@@ -30,7 +30,7 @@ cudaError_t launch_ntt(int limb_bits, int log2_degree, int mode, const NttLaunch
 
 bool ntt_supported(int limb_bits, int n) {
   switch (limb_bits) {
-    case 64: return n >= 2 && n <= 14;
+    case 64: return n >= 2 && n <= 20;
     case 32: return n >= 3 && n <= 15;
     case 16: return n >= 4 && n <= 9;
   }
@@ -170,7 +170,7 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
     return NFLGPU_ERR_ARG;
   }
   if (!ntt_supported(limb_bits, n)) {
-    set_error("unsupported (limb_bits, degree): kernels cover 2^2..2^14 (64-bit), 2^3..2^15 (32-bit), 2^4..2^9 (16-bit)");
+    set_error("unsupported (limb_bits, degree): kernels cover 2^2..2^20 (64-bit), 2^3..2^15 (32-bit), 2^4..2^9 (16-bit)");
     return NFLGPU_ERR_UNSUPPORTED;
   }
   int ndev = 0;

@@ -50,11 +50,15 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int e = plan_e(n, WB);
   static constexpr int E = 1 << e;
   static constexpr int NP = plan_npass(n, WB);
-  static constexpr int TPU = N >> e;  // threads per unit
-  static constexpr int VEC = 16 / (int)sizeof(Word);   // words per 16-byte shared-memory vector
-  static constexpr int PADW = VEC;                      // 16 bytes of padding per row of E words
+  static constexpr int SPLIT = plan_split(n, WB);        // leading passes run as global-memory kernels (0 unless N is huge)
+  static constexpr int LOGB = plan_hi(n, WB, SPLIT);     // the tile kernel transforms sub-blocks of B = 2^LOGB words
+  static constexpr int B = 1 << LOGB;
+  static constexpr int LOGG = n - LOGB;                  // sub-blocks per unit = 2^LOGG
+  static constexpr int TPU = B >> e;                     // threads per sub-block (per unit when SPLIT == 0)
+  static constexpr int VEC = 16 / (int)sizeof(Word);    // words per 16-byte shared-memory vector
+  static constexpr int PADW = VEC;                       // 16 bytes of padding per row of E words
   static constexpr int ROW = E + PADW;
-  static constexpr int TILE_WORDS = (NP > 1) ? (N >> e) * ROW : 0;
+  static constexpr int TILE_WORDS = (NP - SPLIT > 1) ? (B >> e) * ROW : 0;
   // CTA size: 256 threads (2+ CTAs per SM); 512 for N = 1024 x 64-bit (8 two-warp units per CTA, measured best)
 #ifdef NFLGPU_TARGET_THREADS
   static constexpr int TARGET_THREADS = NFLGPU_TARGET_THREADS;
@@ -68,10 +72,11 @@ template <int LB, int LOGN> struct NttCfg {
 #else
   static constexpr int MIN_BLOCKS = (LB == 64 && LOGN == 10) ? 2 : (THREADS <= 256) ? ((WB == 32 && E <= 32) ? 4 : 2) : 1;
 #endif
-  static constexpr bool TW_SMEM = (size_t)N * sizeof(TW) <= 32768;
+  static constexpr bool TW_SMEM = SPLIT == 0 && (size_t)N * sizeof(TW) <= 32768;
   static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)N * sizeof(TW) : 0;
   static constexpr size_t SMEM_BYTES = TW_BYTES + 16 /* mbarrier */ + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
-  static __device__ __forceinline__ int pad(int pos) { return pos + (pos >> e) * PADW; }
+  // tile address of a position (only its offset inside the sub-block matters)
+  static __device__ __forceinline__ int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------
@@ -171,7 +176,8 @@ template <class C, int PASS> __device__ __forceinline__ void inv_pass(typename C
   }
 }
 
-// position of register k of thread `tid` in pass PASS
+// position (inside the unit) of register k of thread `tid` in pass PASS; `tid` is the thread's index inside the whole
+// unit: for split transforms (sub-block number << log2(TPU)) | index inside the sub-block
 template <class C, int PASS> __device__ __forceinline__ int pass_pos(int tid, int k) {
   constexpr int hi = plan_hi(C::n, C::WB, PASS), c = plan_c(C::n, C::WB, PASS);
   const int g = tid >> c, l = tid & ((1 << c) - 1);
@@ -187,7 +193,7 @@ template <class C, int PASS> __device__ __forceinline__ void tile_load(typename 
   typedef typename C::Word Word;
   constexpr int c = plan_c(C::n, C::WB, PASS);
   if (c == 0) {
-    const uint4 *row = reinterpret_cast<const uint4 *>(tile + tid * C::ROW);
+    const uint4 *row = reinterpret_cast<const uint4 *>(tile + (tid & (C::TPU - 1)) * C::ROW);
 #pragma unroll
     for (int v = 0; v < C::E / C::VEC; ++v) {
       uint4 t = row[v];
@@ -204,7 +210,7 @@ template <class C, int PASS> __device__ __forceinline__ void tile_store(const ty
   typedef typename C::Word Word;
   constexpr int c = plan_c(C::n, C::WB, PASS);
   if (c == 0) {
-    uint4 *row = reinterpret_cast<uint4 *>(tile + tid * C::ROW);
+    uint4 *row = reinterpret_cast<uint4 *>(tile + (tid & (C::TPU - 1)) * C::ROW);
 #pragma unroll
     for (int v = 0; v < C::E / C::VEC; ++v) {
       uint4 t;
@@ -223,7 +229,7 @@ template <class C, int PASS> __device__ __forceinline__ void tile_store(const ty
 template <class C> __device__ __forceinline__ void tile_to_gmem(const typename C::Word *tile, typename C::Store *g, int tid) {
   typedef typename C::Word Word;
   typedef typename C::Store Store;
-  constexpr int CHUNKS = C::N / C::VEC;
+  constexpr int CHUNKS = C::B / C::VEC;
 #pragma unroll
   for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
     const int ch = tid + j * C::TPU;
@@ -247,7 +253,7 @@ template <class C, int LB> __device__ __forceinline__ void tile_to_gmem_mul(cons
                                                                             uint64_t k) {
   typedef typename C::Word Word;
   typedef typename C::Store Store;
-  constexpr int CHUNKS = C::N / C::VEC;
+  constexpr int CHUNKS = C::B / C::VEC;
 #pragma unroll
   for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
     const int ch = tid + j * C::TPU;
@@ -276,7 +282,7 @@ template <class C, int LB> __device__ __forceinline__ void tile_to_gmem_mul(cons
 template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word *tile, const typename C::Store *g, int tid) {
   typedef typename C::Word Word;
   typedef typename C::Store Store;
-  constexpr int CHUNKS = C::N / C::VEC;
+  constexpr int CHUNKS = C::B / C::VEC;
 #pragma unroll
   for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
     const int ch = tid + j * C::TPU;
@@ -295,7 +301,7 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
 
 // ---- pass chains (compile-time recursion over the passes) ---------------------------------------------------
 
-// forward: passes 1 .. NP-1 after pass 0 has stored its result into the tile
+// forward: passes SPLIT+1 .. NP-1 after pass SPLIT has stored its result into the tile
 template <class C, int PASS> struct FwdChain {
   static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
                                              typename C::Word p, typename C::Word np, typename C::Word twop, int tid, int slot,
@@ -316,7 +322,7 @@ template <class C> struct FwdChain<C, C::NP> {
                                              typename C::Word, typename C::Word, int, int, int) {}
 };
 
-// inverse: passes NP-1 .. 1 (tile -> registers -> tile); pass 0 is done by the kernel body
+// inverse: passes NP-1 .. SPLIT+1 (tile -> registers -> tile); pass SPLIT is done by the kernel body
 template <class C, int PASS> struct InvChain {
   static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
                                              typename C::Word p, typename C::Word np, typename C::Word twop, const typename C::TW ninv,
@@ -328,7 +334,7 @@ template <class C, int PASS> struct InvChain {
     InvChain<C, PASS - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
   }
 };
-template <class C> struct InvChain<C, 0> {
+template <class C> struct InvChain<C, C::SPLIT> {
   static __device__ __forceinline__ void run(typename C::Word (&)[C::E], typename C::Word *, const typename C::TW *, typename C::Word,
                                              typename C::Word, typename C::Word, const typename C::TW, int, int, int) {}
 };
@@ -360,37 +366,43 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   typedef typename C::Word Word;
   typedef typename C::Store Store;
   typedef typename C::TW TW;
+  constexpr int S = C::SPLIT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const TW *tw = stage_twiddles<C>(a, cm, smem);
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
-  const int slot = threadIdx.x / C::TPU, tid = threadIdx.x % C::TPU;
-  const int lane_base = (threadIdx.x & 31) - (tid & 31);
+  const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
+  const int lane_base = (threadIdx.x & 31) - (tl & 31);
   Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
   const Store *src = reinterpret_cast<const Store *>(a.src);
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
-  for (uint32_t b = rank * C::SLOTS + slot; b < a.batch; b += a.ctas_per_residue * C::SLOTS) {
+  // one iteration = one sub-block (= one whole unit when SPLIT == 0)
+  const uint64_t nblocks = (uint64_t)a.batch << C::LOGG;
+  for (uint64_t j = (uint64_t)rank * C::SLOTS + slot; j < nblocks; j += (uint64_t)a.ctas_per_residue * C::SLOTS) {
+    const uint32_t b = (uint32_t)(j >> C::LOGG), g = (uint32_t)(j & ((1u << C::LOGG) - 1));
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
+    const int tid = (int)(g * C::TPU) + tl;  // index inside the whole unit
     Word x[C::E];
-    // pass 0 reads straight from global memory: for fixed k the unit's threads touch consecutive limbs
+    // the first tile pass reads straight from global memory: for fixed k the threads touch consecutive limbs
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, 0>(tid, k));
-    fwd_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), np, twop);
-    if (C::NP == 1) {
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, S>(tid, k));
+    fwd_pass<C, S>(x, pass_tw<C, S>(tw, tid), np, twop);
+    if (C::NP - S == 1) {
 #pragma unroll
       for (int k = 0; k < C::E; ++k) {
         Word v = csub_lazy(csub_lazy(x[k], twop), p);
-        if (MUL) v = PW<LB>::mulmod(v, (Word)__ldg(reinterpret_cast<const Store *>(a.other) + ubase + pass_pos<C, 0>(tid, k)), p, a.consts[cm]);
-        dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)v;
+        if (MUL) v = PW<LB>::mulmod(v, (Word)__ldg(reinterpret_cast<const Store *>(a.other) + ubase + pass_pos<C, S>(tid, k)), p, a.consts[cm]);
+        dst[ubase + pass_pos<C, S>(tid, k)] = (Store)v;
       }
     } else {
-      unit_sync<C>(slot, lane_base);  // previous unit's copy-out has finished reading the tile
-      tile_store<C, 0>(x, tile, tid);
-      FwdChain<C, 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
+      const size_t bbase = ubase + (size_t)g * C::B;
+      unit_sync<C>(slot, lane_base);  // previous sub-block's copy-out has finished reading the tile
+      tile_store<C, S>(x, tile, tid);
+      FwdChain<C, S + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
-      if (MUL) tile_to_gmem_mul<C, LB>(tile, dst + ubase, reinterpret_cast<const Store *>(a.other) + ubase, tid, p, a.consts[cm]);
-      else tile_to_gmem<C>(tile, dst + ubase, tid);
+      if (MUL) tile_to_gmem_mul<C, LB>(tile, dst + bbase, reinterpret_cast<const Store *>(a.other) + bbase, tl, p, a.consts[cm]);
+      else tile_to_gmem<C>(tile, dst + bbase, tl);
     }
   }
 }
@@ -401,34 +413,67 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   typedef typename C::Word Word;
   typedef typename C::Store Store;
   typedef typename C::TW TW;
+  constexpr int S = C::SPLIT;
   extern __shared__ __align__(128) unsigned char smem[];
   const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const TW *tw = stage_twiddles<C>(a, cm, smem);
   const TW ninv = tw[C::N - 1];
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
-  const int slot = threadIdx.x / C::TPU, tid = threadIdx.x % C::TPU;
-  const int lane_base = (threadIdx.x & 31) - (tid & 31);
+  const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
+  const int lane_base = (threadIdx.x & 31) - (tl & 31);
   Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
   const Store *src = reinterpret_cast<const Store *>(a.src);
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
-  for (uint32_t b = rank * C::SLOTS + slot; b < a.batch; b += a.ctas_per_residue * C::SLOTS) {
+  const uint64_t nblocks = (uint64_t)a.batch << C::LOGG;
+  for (uint64_t j = (uint64_t)rank * C::SLOTS + slot; j < nblocks; j += (uint64_t)a.ctas_per_residue * C::SLOTS) {
+    const uint32_t b = (uint32_t)(j >> C::LOGG), g = (uint32_t)(j & ((1u << C::LOGG) - 1));
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
+    const int tid = (int)(g * C::TPU) + tl;
     Word x[C::E];
-    if (C::NP == 1) {
+    if (C::NP - S == 1) {
 #pragma unroll
-      for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, 0>(tid, k));
+      for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, S>(tid, k));
     } else {
-      unit_sync<C>(slot, lane_base);  // previous unit's pass 0 has finished reading the tile
-      gmem_to_tile<C>(tile, src + ubase, tid);
+      unit_sync<C>(slot, lane_base);  // previous sub-block's last pass has finished reading the tile
+      gmem_to_tile<C>(tile, src + ubase + (size_t)g * C::B, tl);
       InvChain<C, C::NP - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
-      tile_load<C, 0>(x, tile, tid);
+      tile_load<C, S>(x, tile, tid);
     }
-    inv_pass<C, 0>(x, pass_tw<C, 0>(tw, tid), p, np, twop, ninv);
-    // pass 0 writes straight to global memory (lane-contiguous for fixed k)
+    inv_pass<C, S>(x, pass_tw<C, S>(tw, tid), p, np, twop, ninv);
+    // this pass writes straight to global memory (lane-contiguous for fixed k)
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(tid, k)] = (Store)x[k];
+    for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, S>(tid, k)] = (Store)x[k];
+  }
+}
+
+// Global-memory pass PASS (< SPLIT) of a split transform: every thread owns the E coefficients of one butterfly
+// network of this pass (they are 2^c words apart), so the pass needs no exchange: registers <-> HBM, in place on dst.
+template <int LB, int LOGN, int PASS, bool INV>
+__global__ void __launch_bounds__(256) ntt_gpass_kernel(const NttArgs a) {
+  typedef NttCfg<LB, LOGN> C;
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  typedef typename C::TW TW;
+  constexpr int LOGT = C::n - C::e;  // threads per unit
+  const Store *src = reinterpret_cast<const Store *>(a.src);
+  Store *dst = reinterpret_cast<Store *>(a.dst);
+  const uint64_t total = ((uint64_t)a.batch * a.nmoduli) << LOGT;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t u = t >> LOGT;
+    const int tid = (int)(t & ((1u << LOGT) - 1));
+    const int cm = (int)(u % a.nmoduli);
+    const TW *tw = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::N;
+    const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
+    const size_t ubase = (size_t)u * C::N;
+    Word x[C::E];
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, PASS>(tid, k));
+    if (INV) inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, np, twop, __ldg(tw + C::N - 1));
+    else fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, PASS>(tid, k)] = (Store)x[k];
   }
 }
 

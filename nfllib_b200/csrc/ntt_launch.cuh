@@ -6,6 +6,23 @@
 
 namespace nflgpu {
 
+// launches the global-memory passes [FIRST, LAST] of a split transform, ascending (forward) or descending (inverse)
+template <int LB, int LOGN, int PASS, bool INV> cudaError_t launch_gpasses(NttArgs a, int last, int num_sms, cudaStream_t stream) {
+  typedef NttCfg<LB, LOGN> C;
+  if constexpr (PASS >= 0 && PASS < C::SPLIT) {
+    const uint64_t total = ((uint64_t)a.batch * a.nmoduli) << (C::n - C::e);
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > (uint64_t)num_sms * 16) blocks = (uint64_t)num_sms * 16;
+    ntt_gpass_kernel<LB, LOGN, PASS, INV><<<(unsigned)blocks, 256, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || PASS == last) return e;
+    a.src = a.dst;  // later passes work in place on dst
+    return launch_gpasses<LB, LOGN, INV ? PASS - 1 : PASS + 1, INV>(a, last, num_sms, stream);
+  } else {
+    return cudaSuccess;
+  }
+}
+
 // MODE: 0 forward, 1 inverse, 2 forward with the fused "* other" epilogue
 template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
   typedef NttCfg<LB, LOGN> C;
@@ -29,14 +46,25 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
   const uint32_t resident = (uint32_t)num_sms * blocks_per_sm[device];
   uint32_t cpr = resident / l.nmoduli;
   if (cpr == 0) cpr = 1;
-  const uint32_t need = (l.batch + C::SLOTS - 1) / C::SLOTS;
-  if (cpr > need) cpr = need;
+  const uint64_t need = ((((uint64_t)l.batch) << C::LOGG) + C::SLOTS - 1) / C::SLOTS;
+  if (cpr > need) cpr = (uint32_t)need;
   NttArgs a;
   a.src = l.src; a.dst = l.dst; a.tw = l.tw; a.moduli = l.moduli;
   a.nmoduli = l.nmoduli; a.batch = l.batch; a.ctas_per_residue = cpr;
   a.other = l.other; a.consts = l.consts;
+  if constexpr (C::SPLIT > 0 && MODE != 1) {  // forward: global passes 0 .. SPLIT-1 (src -> dst), then the tile kernel in place
+    cudaError_t e = launch_gpasses<LB, LOGN, 0, false>(a, C::SPLIT - 1, num_sms, stream);
+    if (e != cudaSuccess) return e;
+    a.src = a.dst;
+  }
   kernel<<<cpr * l.nmoduli, C::THREADS, C::SMEM_BYTES, stream>>>(a);
-  return cudaGetLastError();
+  cudaError_t e = cudaGetLastError();
+  if constexpr (C::SPLIT > 0 && MODE == 1) {  // inverse: tile kernel (src -> dst), then global passes SPLIT-1 .. 0 in place
+    if (e != cudaSuccess) return e;
+    a.src = a.dst;
+    e = launch_gpasses<LB, LOGN, C::SPLIT - 1, true>(a, 0, num_sms, stream);
+  }
+  return e;
 }
 
 }  // namespace nflgpu

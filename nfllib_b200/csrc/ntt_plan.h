@@ -54,5 +54,16 @@ NFLGPU_HD constexpr int plan_c(int n, int word_bits, int i) { return plan_hi(n, 
 // offset of pass i in the twiddle table: sum over earlier stages of 2^s = 2^s0 - 1
 NFLGPU_HD constexpr int plan_off(int n, int word_bits, int i) { return (1 << plan_s0(n, word_bits, i)) - 1; }
 
+// Transforms too large for one shared-memory tile (64-bit words: N > 2^14) run their first `split` passes as
+// global-memory passes (one kernel each, registers <-> HBM, no exchange needed because a pass's E coefficients live in
+// one thread); after them the unit has decomposed into 2^s0 independent sub-blocks of 2^hi words, each of which the
+// tile kernel finishes exactly like a small transform (its twiddles are indexed by the sub-block number).
+NFLGPU_HD constexpr int plan_tile_log(int word_bits) { return word_bits == 64 ? 14 : 15; }
+NFLGPU_HD constexpr int plan_split(int n, int word_bits) {
+  int s = 0;
+  while (plan_hi(n, word_bits, s) > plan_tile_log(word_bits)) ++s;
+  return s;
+}
+
 }  // namespace nflgpu
 #endif

@@ -57,13 +57,15 @@ def test_reference_fixtures(path):
     assert np.array_equal(c.run_device("muladd", a, b, k["fwd_a"]), k["muladd"])
 
 
-SIZES = [(64, n) for n in range(2, 15)] + [(32, n) for n in range(3, 16)] + [(16, n) for n in range(4, 10)]
+SIZES = [(64, n) for n in range(2, 21)] + [(32, n) for n in range(3, 16)] + [(16, n) for n in range(4, 10)]
 
 
 @pytest.mark.parametrize("bits,n", SIZES, ids=[f"u{b}_n{n}" for b, n in SIZES])
 def test_all_sizes_vs_oracle(bits, n):
     N = 1 << n
-    for M, batch in ((1, 3), (2 if bits == 16 else 3, 37 if N <= 4096 else 5)):
+    # n >= 15 (64-bit) exercises the split path: global-memory passes + tile kernel over sub-blocks (ntt_plan.h)
+    cases = ((1, 3), (2 if bits == 16 else 3, 37 if N <= 4096 else 5)) if n <= 15 else ((1, 2), (2, 3))
+    for M, batch in cases:
         o = Oracle(bits, N, M)
         c = ctx_for(bits, N, M)
         a = random_polys(bits, N, M, batch, 31 * n + M)
@@ -80,7 +82,7 @@ def test_all_sizes_vs_oracle(bits, n):
         assert np.array_equal(c.run_device("mul_shoup", a, b, bs), o.run("mul_shoup", a, b, bs))
         assert np.array_equal(c.run_device("muladd", a, b, fa), o.run("muladd", a, b, fa))
         assert np.array_equal(c.run_device("muladd_shoup", fa, a, b, bs), o.run("add", fa, o.run("mul_shoup", a, b, bs)))
-        if N <= 4096:
+        if N <= 4096 or n >= 15:
             assert np.array_equal(c.run_device("polymul", a, b), o.run("polymul", a, b))
 
 
@@ -161,7 +163,8 @@ def test_host_op_matches_device_path():
 
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so did not travel")
 def test_live_reference_side_by_side():
-    for bits, N, M in ((64, 1024, 4), (64, 16384, 8), (32, 4096, 14), (64, 8192, 6), (16, 512, 2)):
+    # (64, 32768, 2) is the largest configuration of the reference's own test matrix (tests/CMakeLists.txt:1-7)
+    for bits, N, M in ((64, 1024, 4), (64, 16384, 8), (32, 4096, 14), (64, 8192, 6), (16, 512, 2), (64, 32768, 2), (32, 32768, 1)):
         r, c = Ref(bits, N, M), ctx_for(bits, N, M)
         a = random_polys(bits, N, M, 6, 99)
         b = random_polys(bits, N, M, 6, 98)
@@ -188,7 +191,7 @@ def test_errors_and_empty():
     with pytest.raises(nb.NflGpuError):
         nb.Context(16, 512, 3)  # nmoduli > params<uint16_t>::kMaxNbModuli
     with pytest.raises(nb.NflGpuError):
-        nb.Context(64, 32768, 1)  # beyond the kernels' shared-memory tile
+        nb.Context(64, 1 << 21, 1)  # degree > params<uint64_t>::kMaxPolyDegree
 
 
 def test_first_modulus_window_matches_residue_slice():
