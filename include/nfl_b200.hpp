@@ -118,6 +118,7 @@ namespace simd { struct cuda {}; }
 struct uniform {};  // poly.hpp:42 — test-grade here (std::mt19937_64), NOT the reference's Salsa20 stream
 
 template <class T, size_t Degree, size_t NbModuli> class poly;
+template <class T, size_t Degree, size_t NbModuli> class poly_p;
 
 // ---------------------------------------------------------------------------------------------------------
 // Backend: one nflgpu context per (T, Degree, NbModuli), created on first use (the reference builds its
@@ -151,8 +152,9 @@ template <class P> struct dev_buf {
 }  // namespace detail
 
 // ---------------------------------------------------------------------------------------------------------
-// Expression templates (ops.hpp:47-277).  Nodes are evaluated on the device: leaves are uploaded, every functor
-// is one kernel, `shoup(a*b, b')` is rewritten to mulmod_shoup (ops.hpp:266-277) and `x + y*z` to the fused muladd.
+// Expression templates (ops.hpp:47-277).  A whole tree is flattened into a postfix program and evaluated by ONE kernel
+// (nflgpu_eval): every leaf is uploaded and read once, as in the reference's fused evaluator loop; `shoup(a*b, b')` is
+// rewritten to mulmod_shoup (ops.hpp:266-277).  Trees beyond nflgpu_eval's limits fall back to one kernel per node.
 // ---------------------------------------------------------------------------------------------------------
 namespace ops {
 
@@ -182,6 +184,9 @@ template <class P> struct operand_eval<P, P> {
     check(nflgpu_upload(P::backend_type::get().ctx, b->p, x.data(), 1, nullptr), "nflgpu_upload");
     return b;
   }
+};
+template <class T, size_t D, size_t M> struct operand_eval<poly<T, D, M>, poly_p<T, D, M>> {
+  static std::unique_ptr<dev_buf<poly<T, D, M>>> run(poly_p<T, D, M> const &x) { return operand_eval<poly<T, D, M>, poly<T, D, M>>::run(x.poly_obj()); }
 };
 
 #define NFLB200_BIN(OPTAG, CALL)                                                                                    \
@@ -233,8 +238,73 @@ template <class P, class A0> struct operand_eval<P, ops::expr<ops::compute_shoup
   }
 };
 
+// ---- fused path: flatten the tree into the postfix program of nflgpu_eval (one kernel, every leaf read once) ----
+template <class P> struct rpn {
+  std::vector<const P *> leaves;
+  std::vector<uint8_t> prog;
+  int depth, max_depth;
+  bool ok;
+  rpn() : depth(0), max_depth(0), ok(true) {}
+  void leaf(const P &p) {
+    size_t i = 0;
+    while (i < leaves.size() && leaves[i] != &p) ++i;   // the same poly appearing twice is uploaded once
+    if (i == leaves.size()) { if (leaves.size() == 8) { ok = false; return; } leaves.push_back(&p); }
+    prog.push_back(static_cast<uint8_t>(i));
+    if (++depth > max_depth) max_depth = depth;
+  }
+  void op(uint8_t tok, int pops) { prog.push_back(tok); depth -= pops - 1; }
+};
+template <class P, class X> struct emit;
+template <class P> struct emit<P, P> { static void run(rpn<P> &r, P const &x) { r.leaf(x); } };
+template <class T, size_t D, size_t M> struct emit<poly<T, D, M>, poly_p<T, D, M>> {
+  static void run(rpn<poly<T, D, M>> &r, poly_p<T, D, M> const &x) { r.leaf(x.poly_obj()); }
+};
+#define NFLB200_EMIT_BIN(OPTAG, TOK)                                                             \
+  template <class P, class A0, class A1> struct emit<P, ops::expr<ops::OPTAG, A0, A1>> {        \
+    static void run(rpn<P> &r, ops::expr<ops::OPTAG, A0, A1> const &e) {                         \
+      emit<P, A0>::run(r, std::get<0>(e.args)); emit<P, A1>::run(r, std::get<1>(e.args)); r.op(TOK, 2); \
+    }                                                                                            \
+  };
+NFLB200_EMIT_BIN(addmod, 0x10)
+NFLB200_EMIT_BIN(submod, 0x11)
+NFLB200_EMIT_BIN(mulmod, 0x12)
+#undef NFLB200_EMIT_BIN
+template <class P, class A0, class A1, class A2> struct emit<P, ops::expr<ops::mulmod_shoup, A0, A1, A2>> {
+  static void run(rpn<P> &r, ops::expr<ops::mulmod_shoup, A0, A1, A2> const &e) {
+    emit<P, A0>::run(r, std::get<0>(e.args)); emit<P, A1>::run(r, std::get<1>(e.args)); emit<P, A2>::run(r, std::get<2>(e.args));
+    r.op(0x13, 3);
+  }
+};
+template <class P, class A0> struct emit<P, ops::expr<ops::compute_shoup, A0>> {
+  static void run(rpn<P> &r, ops::expr<ops::compute_shoup, A0> const &e) { emit<P, A0>::run(r, std::get<0>(e.args)); r.op(0x14, 1); }
+};
+
+// Evaluates `e` into host poly `out`: fused single kernel when the tree fits nflgpu_eval's limits, node by node otherwise.
+template <class P, class X> void assign_expr(P &out, X const &e) {
+  nflgpu_ctx *ctx = P::backend_type::get().ctx;
+  rpn<P> r;
+  emit<P, X>::run(r, e);
+  if (r.ok && r.prog.size() <= 32 && r.max_depth <= 8) {
+    std::vector<std::unique_ptr<dev_buf<P>>> bufs;
+    std::vector<const void *> ptrs;
+    for (size_t i = 0; i < r.leaves.size(); ++i) {
+      bufs.emplace_back(new dev_buf<P>(1));
+      check(nflgpu_upload(ctx, bufs.back()->p, r.leaves[i]->data(), 1, nullptr), "nflgpu_upload");
+      ptrs.push_back(bufs.back()->p);
+    }
+    check(nflgpu_eval(ctx, bufs[0]->p, ptrs.data(), ptrs.size(), r.prog.data(), r.prog.size(), 1, nullptr), "nflgpu_eval");
+    check(nflgpu_download(ctx, out.data(), bufs[0]->p, 1, nullptr), "nflgpu_download");
+    check(nflgpu_sync(ctx, nullptr), "nflgpu_sync");
+    return;
+  }
+  auto res = operand_eval<P, X>::run(e);
+  check(nflgpu_download(ctx, out.data(), res->p, 1, nullptr), "nflgpu_download");
+  check(nflgpu_sync(ctx, nullptr), "nflgpu_sync");
+}
+
 template <class X> struct is_operand : std::false_type {};
 template <class T, size_t D, size_t M> struct is_operand<poly<T, D, M>> : std::true_type {};
+template <class T, size_t D, size_t M> struct is_operand<poly_p<T, D, M>> : std::true_type {};
 template <class Op, class... A> struct is_operand<ops::expr<Op, A...>> : std::true_type {};
 
 }  // namespace detail
@@ -304,10 +374,7 @@ public:
   poly &operator=(uniform const &mode) { set(mode); return *this; }
   poly &operator=(std::initializer_list<value_type> values) { set(values); return *this; }
   template <class Op, class... Args> poly &operator=(ops::expr<Op, Args...> const &e) {  // core.hpp:24-37
-    auto r = detail::operand_eval<poly, ops::expr<Op, Args...>>::run(e);
-    nflgpu_ctx *ctx = backend_type::get().ctx;
-    detail::check(nflgpu_download(ctx, _data, r->p, 1, nullptr), "nflgpu_download");
-    detail::check(nflgpu_sync(ctx, nullptr), "nflgpu_sync");
+    detail::assign_expr<poly, ops::expr<Op, Args...>>(*this, e);
     return *this;
   }
 
@@ -337,6 +404,68 @@ template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::degree;
 template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::nmoduli;
 template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::nbits;
 template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::aggregated_modulus_bit_size;
+
+// ---------------------------------------------------------------------------------------------------------
+// poly_p  (poly_p.hpp:11-204): shared, copy-on-write handle to a 32-byte aligned heap poly.  Copies are O(1); the first
+// mutating access through a shared handle clones the coefficients (poly_p.hpp:176-183).  Takes part in expressions
+// exactly like a poly (tests/poly_p.cpp).
+// ---------------------------------------------------------------------------------------------------------
+template <class T, size_t Degree, size_t NbModuli> class poly_p {
+public:
+  typedef poly<T, Degree, NbModuli> poly_type;
+  typedef typename poly_type::backend_type backend_type;
+  using value_type = typename poly_type::value_type;
+  using greater_value_type = typename poly_type::greater_value_type;
+  static constexpr size_t nmoduli = poly_type::nmoduli;
+  static constexpr size_t degree = poly_type::degree;
+  static constexpr size_t nbits = poly_type::nbits;
+  static constexpr size_t aggregated_modulus_bit_size = poly_type::aggregated_modulus_bit_size;
+
+private:
+  std::shared_ptr<poly_type> p_;
+  template <class... Args> static std::shared_ptr<poly_type> make(Args &&... args) {
+    void *raw = nullptr;
+    if (posix_memalign(&raw, 32, sizeof(poly_type)) != 0) throw std::bad_alloc();
+    poly_type *obj;
+    try { obj = new (raw) poly_type(std::forward<Args>(args)...); } catch (...) { free(raw); throw; }
+    return std::shared_ptr<poly_type>(obj, [](poly_type *q) { q->~poly_type(); free(q); });
+  }
+  void detach() { if (p_.use_count() > 1) p_ = make(p_->begin(), p_->end(), false); }
+
+public:
+  poly_p() : p_(make()) {}
+  poly_p(poly_p const &o) : p_(o.p_) {}
+  poly_p(poly_p &o) : p_(o.p_) {}
+  poly_p(poly_p &&o) : p_(std::move(o.p_)) {}
+  poly_p(std::initializer_list<value_type> values) : p_(make(values)) {}
+  template <class A0, class... Args> poly_p(A0 &&a0, Args &&... args) : p_(make(std::forward<A0>(a0), std::forward<Args>(args)...)) {}
+
+  poly_type &poly_obj() { detach(); return *p_; }
+  poly_type const &poly_obj() const { return *p_; }
+
+  poly_p &operator=(poly_p const &o) { p_ = o.p_; return *this; }
+  poly_p &operator=(poly_p &&o) { p_ = std::move(o.p_); return *this; }
+  poly_p &operator=(std::initializer_list<value_type> values) { poly_obj() = values; return *this; }
+  template <class O> poly_p &operator=(O &&o) { poly_obj() = std::forward<O>(o); return *this; }
+
+  value_type &operator()(size_t cm, size_t i) { return poly_obj()(cm, i); }
+  value_type const &operator()(size_t cm, size_t i) const { return poly_obj()(cm, i); }
+  typename poly_type::iterator begin() { return poly_obj().begin(); }
+  typename poly_type::iterator end() { return poly_obj().end(); }
+  typename poly_type::const_iterator begin() const { return poly_obj().begin(); }
+  typename poly_type::const_iterator end() const { return poly_obj().end(); }
+  typename poly_type::pointer_type data() { return poly_obj().data(); }
+  static value_type get_modulus(size_t n) { return poly_type::get_modulus(n); }
+  void ntt_pow_phi() { poly_obj().ntt_pow_phi(); }
+  void invntt_pow_invphi() { poly_obj().invntt_pow_invphi(); }
+  template <class... Args> void set(Args &&... args) { poly_obj().set(std::forward<Args>(args)...); }
+  void serialize_manually(std::ostream &os) { poly_obj().serialize_manually(os); }
+  void deserialize_manually(std::istream &is) { poly_obj().deserialize_manually(is); }
+};
+template <class T, size_t D, size_t M> constexpr size_t poly_p<T, D, M>::degree;
+template <class T, size_t D, size_t M> constexpr size_t poly_p<T, D, M>::nmoduli;
+template <class T, size_t Degree, size_t AggregatedModulusBitSize>
+using poly_p_from_modulus = poly_p<T, Degree, AggregatedModulusBitSize / params<T>::kModulusBitsize>;
 
 /* operator overloads (poly.hpp:346-352 via the macros of ops.hpp:18-45) */
 #define NFLB200_DECLARE_BINARY(NAME, TAG)                                                                                   \
@@ -374,8 +503,14 @@ template <class P> struct aligned_holder {
   aligned_holder &operator=(const aligned_holder &) = delete;
 };
 // materialise an operand on the host (used only by the boolean comparisons, which are not on the hot path)
-template <class P> P const &host_value(P const &p, P &) { return p; }
-template <class P, class Op, class... A> P const &host_value(ops::expr<Op, A...> const &e, P &tmp) { tmp = e; return tmp; }
+template <class P, class X> struct host_value;
+template <class P> struct host_value<P, P> { static P const &get(P const &p, P &) { return p; } };
+template <class T, size_t D, size_t M> struct host_value<poly<T, D, M>, poly_p<T, D, M>> {
+  static poly<T, D, M> const &get(poly_p<T, D, M> const &p, poly<T, D, M> &) { return p.poly_obj(); }
+};
+template <class P, class Op, class... A> struct host_value<P, ops::expr<Op, A...>> {
+  static P const &get(ops::expr<Op, A...> const &e, P &tmp) { tmp = e; return tmp; }
+};
 }  // namespace detail
 
 namespace ops {
@@ -383,8 +518,10 @@ template <class Op, class... Args> expr<Op, Args...>::operator bool() const {
   static_assert(std::is_same<Op, eqmod>::value || std::is_same<Op, neqmod>::value, "only == and != convert to bool (ops.hpp:81-95)");
   typedef poly_type P;
   detail::aligned_holder<P> ta, tb;
-  P const &a = detail::host_value<P>(std::get<0>(args), *ta.p);
-  P const &b = detail::host_value<P>(std::get<1>(args), *tb.p);
+  typedef typename std::tuple_element<0, std::tuple<Args...>>::type X0;
+  typedef typename std::tuple_element<1, std::tuple<Args...>>::type X1;
+  P const &a = detail::host_value<P, X0>::get(std::get<0>(args), *ta.p);
+  P const &b = detail::host_value<P, X1>::get(std::get<1>(args), *tb.p);
   const bool want_equal = std::is_same<Op, eqmod>::value;
   for (size_t i = 0; i < P::degree * P::nmoduli; ++i)
     if ((a.begin()[i] == b.begin()[i]) == want_equal) return true;  // ANY coefficient (the reference's semantics)
@@ -441,6 +578,15 @@ public:
   void assign_compute_shoup(batch const &a) { detail::check(nflgpu_compute_shoup(ctx(), buf_.p, a.buf_.p, buf_.count, nullptr), "nflgpu_compute_shoup"); }
   void assign_mul_shoup(batch const &a, batch const &b, batch const &bprime) {
     detail::check(nflgpu_mul_shoup(ctx(), buf_.p, a.buf_.p, b.buf_.p, bprime.buf_.p, buf_.count, nullptr), "nflgpu_mul_shoup");
+  }
+  // *this = <postfix program over operands> in one pass (nflgpu_eval); e.g. {0,1,2,0x12,0x10} = ops[0] + ops[1]*ops[2]
+  void assign_eval(std::vector<batch const *> const &operands, std::vector<uint8_t> const &program) {
+    std::vector<const void *> ptrs;
+    for (size_t i = 0; i < operands.size(); ++i) {
+      if (operands[i]->size() != size()) throw std::runtime_error("nfl::cuda::batch: size mismatch");
+      ptrs.push_back(operands[i]->buf_.p);
+    }
+    detail::check(nflgpu_eval(ctx(), buf_.p, ptrs.data(), ptrs.size(), program.data(), program.size(), buf_.count, nullptr), "nflgpu_eval");
   }
   void assign_muladd(batch const &a, batch const &b, batch const &c) {  // *this = a + b * c
     detail::check(nflgpu_muladd(ctx(), buf_.p, a.buf_.p, b.buf_.p, c.buf_.p, buf_.count, nullptr), "nflgpu_muladd");

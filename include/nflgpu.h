@@ -116,6 +116,18 @@ int nflgpu_muladd(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, cons
 int nflgpu_muladd_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *c,
                         const void *cprime, size_t batch, void *stream);
 
+/* Fused evaluation of an ARBITRARY expression tree in one pass over memory — what the reference's expression
+ * templates do (ops::expr ops.hpp:52-97, _make_op rewrite ops.hpp:249-277, evaluator core.hpp:24-37): `c = a + b*d - e`
+ * reads a, b, d, e once and writes c once.  `program` is the tree in postfix order, one byte per token:
+ *     0x00..0x07  push operands[k]
+ *     0x10 add   0x11 sub   0x12 mul            pop y, pop x, push x (op) y         (addmod / submod / mulmod)
+ *     0x13 mul_shoup                            pop y', pop y, pop x, push x*y       (mulmod_shoup with y' = shoup(y))
+ *     0x14 compute_shoup                        pop x, push floor(x * 2^w / p)
+ * Limits: at most 8 operands, 32 tokens, stack depth 8; the program must leave exactly one value.  dst may alias an
+ * operand. */
+int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t noperands, const uint8_t *program,
+                size_t ntokens, size_t batch, void *stream);
+
 /* ---- fused negacyclic product ---------------------------------------------------------------------------- */
 
 /* dst = invntt_pow_invphi( ntt_pow_phi(a) * ntt_pow_phi(b) )  — the four reference calls of

@@ -55,6 +55,7 @@ def lib():
             getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_muladd_shoup.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_host_op.argtypes = [vp, ci, vp, vp, vp, vp, sz]
+        L.nflgpu_eval.argtypes = [vp, vp, ctypes.POINTER(vp), sz, ctypes.c_char_p, sz, sz, vp]
         _lib = L
     return _lib
 
@@ -152,6 +153,12 @@ class Context:
 
     def muladd_shoup(self, dst, a, b, c, cprime, batch, stream=0):
         _check(lib().nflgpu_muladd_shoup(self.h, dst, a, b, c, cprime, batch, stream))
+
+    def eval(self, dst, operands, program, batch, stream=0):
+        """nflgpu_eval: `operands` = list of device pointers, `program` = postfix bytes (see include/nflgpu.h)."""
+        arr = (ctypes.c_void_p * len(operands))(*operands)
+        prog = bytes(program)
+        _check(lib().nflgpu_eval(self.h, dst, arr, len(operands), prog, len(prog), batch, stream))
 
     def polymul(self, dst, a, b, batch, stream=0):
         _check(lib().nflgpu_polymul(self.h, dst, a, b, batch, stream))

@@ -352,6 +352,48 @@ int nflgpu_muladd_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b
   return run_pw(ctx, PW_MULADD_SHOUP, 4, dst, a, b, c, cprime, batch, stream);
 }
 
+int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t noperands, const uint8_t *program, size_t ntokens,
+                size_t batch, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst, "dst"))) return rc;
+  if (!operands || !program || noperands == 0 || noperands > EV_MAX_OPERANDS || ntokens == 0 || ntokens > EV_MAX_TOKENS) {
+    set_error("nflgpu_eval: need 1..8 operands and 1..32 tokens");
+    return NFLGPU_ERR_ARG;
+  }
+  for (size_t i = 0; i < noperands; ++i)
+    if ((rc = check_buf(ctx, operands[i], "operand"))) return rc;
+  // validate the stack discipline on the host so the kernel never has to
+  int sp = 0;
+  for (size_t t = 0; t < ntokens; ++t) {
+    const uint8_t tok = program[t];
+    int pops, pushes = 1;
+    if (tok < EV_MAX_OPERANDS) { if (tok >= noperands) { set_error("nflgpu_eval: operand index out of range"); return NFLGPU_ERR_ARG; } pops = 0; }
+    else if (tok == EV_ADD || tok == EV_SUB || tok == EV_MUL) pops = 2;
+    else if (tok == EV_MUL_SHOUP) pops = 3;
+    else if (tok == EV_COMPUTE_SHOUP) pops = 1;
+    else { set_error("nflgpu_eval: unknown token"); return NFLGPU_ERR_ARG; }
+    if (sp < pops) { set_error("nflgpu_eval: stack underflow"); return NFLGPU_ERR_ARG; }
+    sp += pushes - pops;
+    if (sp > EV_MAX_STACK) { set_error("nflgpu_eval: expression too deep (stack > 8)"); return NFLGPU_ERR_ARG; }
+  }
+  if (sp != 1) { set_error("nflgpu_eval: program must leave exactly one value"); return NFLGPU_ERR_ARG; }
+  if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  EvArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.dst = dst;
+  for (size_t i = 0; i < noperands; ++i) a.operands[i] = operands[i];
+  a.moduli = ctx->d_moduli64; a.consts = ctx->d_consts;
+  a.nmoduli = (uint32_t)ctx->nmoduli; a.degree = (uint32_t)ctx->degree; a.log2_degree = (uint32_t)ctx->log2_degree;
+  a.batch = (uint32_t)batch; a.ntokens = (uint32_t)ntokens;
+  std::memcpy(a.program, program, ntokens);
+  CUDA_TRY(launch_eval(ctx->limb_bits, a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return NFLGPU_OK;
+}
+
 int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
   int rc;
   if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, a, "a")) || (rc = check_buf(ctx, b, "b"))) return rc;

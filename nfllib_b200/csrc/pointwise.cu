@@ -121,6 +121,74 @@ template <int LB> static cudaError_t launch_limb(int op, const PwArgs &a, int nu
   return cudaErrorInvalidValue;
 }
 
+// ---- fused expression evaluator ---------------------------------------------------------------------------------
+// The reference evaluates a whole expression tree per coefficient in one loop (ops::expr::load recursion, ops.hpp:69-79,
+// driven by core.hpp:24-37).  Here the tree arrives as a postfix program that every thread interprets on a small
+// value stack; the program is uniform across the grid, so the interpreter's branches never diverge and the kernel
+// stays HBM-bound: each operand is read exactly once and the result written once, whatever the tree.
+template <int LB>
+__global__ void __launch_bounds__(256) eval_kernel(const EvArgs a) {
+  typedef typename PW<LB>::Word Word;
+  typedef typename PW<LB>::Store Store;
+  constexpr int VEC = PW<LB>::VEC;
+  const uint32_t cm = blockIdx.y;
+  const Word p = (Word)a.moduli[cm];
+  const uint64_t kc = a.consts[cm];
+  const uint32_t vec_per_row = a.degree / VEC, row_shift = a.log2_degree - (VEC == 2 ? 1 : VEC == 4 ? 2 : 3);
+  const uint64_t total = (uint64_t)a.batch * vec_per_row;
+  Store *dst = reinterpret_cast<Store *>(a.dst);
+  for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t b = v >> row_shift, off = v & (vec_per_row - 1);
+    const size_t at = ((size_t)b * a.nmoduli + cm) * a.degree + off * VEC;
+    Word st[EV_MAX_STACK][VEC];
+    int sp = 0;
+    for (uint32_t t = 0; t < a.ntokens; ++t) {
+      const uint32_t tok = a.program[t];
+      if (tok < EV_MAX_OPERANDS) {
+        VecIO<LB>::load(st[sp], reinterpret_cast<const Store *>(a.operands[tok]) + at);
+        ++sp;
+      } else if (tok == EV_COMPUTE_SHOUP) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) st[sp - 1][i] = Functor<LB, PW_COMPUTE_SHOUP>::apply(st[sp - 1][i], 0, 0, 0, p, kc);
+      } else if (tok == EV_MUL_SHOUP) {
+        sp -= 2;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) st[sp - 1][i] = Functor<LB, PW_MUL_SHOUP>::apply(st[sp - 1][i], st[sp][i], st[sp + 1][i], 0, p, kc);
+      } else {
+        --sp;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const Word x = st[sp - 1][i], y = st[sp][i];
+          st[sp - 1][i] = tok == EV_ADD ? Functor<LB, PW_ADD>::apply(x, y, 0, 0, p, kc)
+                        : tok == EV_SUB ? Functor<LB, PW_SUB>::apply(x, y, 0, 0, p, kc)
+                                        : Functor<LB, PW_MUL>::apply(x, y, 0, 0, p, kc);
+        }
+      }
+    }
+    VecIO<LB>::store(dst + at, st[0]);
+  }
+}
+
+template <int LB> static cudaError_t launch_eval_limb(const EvArgs &a, int num_sms, cudaStream_t stream) {
+  constexpr int VEC = PW<LB>::VEC;
+  const uint64_t total = (uint64_t)a.batch * (a.degree / VEC);
+  if (total == 0) return cudaSuccess;
+  uint64_t blocks = (total + 255) / 256;
+  const uint64_t cap = (uint64_t)num_sms * 8 / a.nmoduli + 1;
+  if (blocks > cap) blocks = cap;
+  eval_kernel<LB><<<dim3((unsigned)blocks, a.nmoduli), 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval(int limb_bits, const EvArgs &a, int num_sms, cudaStream_t stream) {
+  switch (limb_bits) {
+    case 64: return launch_eval_limb<64>(a, num_sms, stream);
+    case 32: return launch_eval_limb<32>(a, num_sms, stream);
+    case 16: return launch_eval_limb<16>(a, num_sms, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
 cudaError_t launch_pointwise(int limb_bits, int op, const PwArgs &a, int num_sms, cudaStream_t stream) {
   switch (limb_bits) {
     case 64: return launch_limb<64>(op, a, num_sms, stream);

@@ -18,5 +18,18 @@ struct PwArgs {
 
 cudaError_t launch_pointwise(int limb_bits, int op, const PwArgs &a, int num_sms, cudaStream_t stream);
 
+// Fused evaluation of a whole expression tree in one pass (postfix program, see nflgpu_eval in include/nflgpu.h).
+enum { EV_MAX_OPERANDS = 8, EV_MAX_TOKENS = 32, EV_MAX_STACK = 8 };
+enum EvTok { EV_ADD = 0x10, EV_SUB = 0x11, EV_MUL = 0x12, EV_MUL_SHOUP = 0x13, EV_COMPUTE_SHOUP = 0x14 };
+struct EvArgs {
+  void *dst;
+  const void *operands[EV_MAX_OPERANDS];
+  const uint64_t *moduli, *consts;
+  uint32_t nmoduli, degree, log2_degree, batch;
+  uint32_t ntokens;
+  uint8_t program[EV_MAX_TOKENS];
+};
+cudaError_t launch_eval(int limb_bits, const EvArgs &a, int num_sms, cudaStream_t stream);
+
 }  // namespace nflgpu
 #endif

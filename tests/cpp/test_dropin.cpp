@@ -61,8 +61,13 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
     e = x + y * x;                                            // nested expression, fused muladd (poly_p.cpp:63-66)
     sum = y * x; sum = x + sum;
     REQUIRE(same(e, sum));
-    e = (x + y) * (x - y) + y * y;                            // = x*x
+    e = (x + y) * (x - y) + y * y;                            // = x*x, 7-token fused program
     sum = x * x;
+    REQUIRE(same(e, sum));
+    e = x + y * x - nfl::shoup(x * y, bs);                    // fused: add, mul, sub, mul_shoup; = x
+    REQUIRE(same(e, x));
+    e = ((((x + y) + (y + x)) + ((x - y) + (y - x))) + (((x * y) + (y * x)) - ((x * y) + (x * y)))) - (y + y);  // = 2x
+    sum = x + x;
     REQUIRE(same(e, sum));
     P c(x.begin(), x.end(), false);                           // iterator ctor, all residues given
     REQUIRE(same(c, x));
@@ -79,6 +84,32 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
     try { std::vector<T> big(P::degree + 1, 1); P bad(big.begin(), big.end()); (void)bad; } catch (std::runtime_error const &) { threw = true; }
     REQUIRE(threw || P::nmoduli == 1);                        // core.hpp:111-115 (degree+1 == degree*nmoduli only if ... never)
     REQUIRE(P::get_modulus(0) == nfl::params<T>::P[0]);
+    // poly_p: same results as poly through the shared handle (tests/poly_p.cpp:12-66, strong comparisons)
+    {
+      typedef nfl::poly_p<T, P::degree, P::nmoduli> PP;
+      PP pa(x.begin(), x.end(), false), pb(y.begin(), y.end(), false);
+      PP psum(pa + pb), pdif(pa - pb), pprd(pa * pb);
+      sum = x + y; dif = x - y;
+      REQUIRE(same(psum.poly_obj(), sum) && same(pdif.poly_obj(), dif) && same(pprd.poly_obj(), prd));
+      PP pc(pb);                                              // shares storage
+      REQUIRE(&static_cast<PP const &>(pc).poly_obj() == &static_cast<PP const &>(pb).poly_obj());
+      pc = {1};                                               // detaches: pb is untouched
+      REQUIRE(same(static_cast<PP const &>(pb).poly_obj(), y) && pc(0, 0) == 1 && pc(0, 1) == 0);
+      PP pbs = nfl::compute_shoup(pb);
+      REQUIRE(same(static_cast<PP const &>(pbs).poly_obj(), bs));
+      PP pmul2 = nfl::shoup(pa * pb, pbs);
+      REQUIRE(same(static_cast<PP const &>(pmul2).poly_obj(), prd));
+      PP pmix = pa + pb * psum;                               // poly_p operands inside a fused expression
+      e = x + y * sum;
+      REQUIRE(same(static_cast<PP const &>(pmix).poly_obj(), e));
+      e = pa + y * psum;                                      // mixed poly / poly_p operands
+      REQUIRE(same(static_cast<PP const &>(pmix).poly_obj(), e));
+      pa.ntt_pow_phi(); c = x; c.ntt_pow_phi();
+      REQUIRE(same(static_cast<PP const &>(pa).poly_obj(), c));
+      pa.invntt_pow_invphi();
+      REQUIRE(same(static_cast<PP const &>(pa).poly_obj(), x));
+      REQUIRE(bool(pa == x) && !bool(pa != x));
+    }
     free(tmp);
   }
 
@@ -106,7 +137,16 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
     t.invntt_pow_invphi(); dump(t);                            // a again
     t.assign_mul(da, db); dump(t);
     u.assign_compute_shoup(db); t.assign_mul_shoup(da, db, u); dump(t);
-    t.assign_muladd(da, db, da); dump(t);                      // a + b*a
+    t.assign_muladd(da, db, da);                               // a + b*a
+    u.assign_eval({&da, &db}, {0, 1, 0, 0x12, 0x10});          // same through the fused evaluator
+    {
+      P *h2 = alloc_polys<P>(count);
+      t.download(h);
+      u.download(h2);
+      for (size_t i = 0; i < count; ++i) { REQUIRE(same(h[i], h2[i])); }
+      free(h2);
+    }
+    dump(t);
     t.assign_polymul(da, db); dump(t);
     free(h);
   }

@@ -203,3 +203,63 @@ def test_first_modulus_window_matches_residue_slice():
     sub = np.ascontiguousarray(a[:, 3:7, :])
     assert np.array_equal(part.run_device("ntt_fwd", sub), fa[:, 3:7, :])
     part.close()
+
+
+def _random_tree(rng, nops, depth):
+    """returns (postfix program, evaluator(oracle, operands) -> array, max stack depth)"""
+    if depth == 0 or rng.random() < 0.25:
+        k = rng.randrange(nops)
+        return [k], (lambda o, ops, k=k: ops[k]), 1
+    kind = rng.choice(["add", "sub", "mul", "mul", "shoup"])
+    lp, lf, ld = _random_tree(rng, nops, depth - 1)
+    if kind == "shoup":  # x * y with y a plain operand and y' = compute_shoup(y) computed inside the program
+        k = rng.randrange(nops)
+        prog = lp + [k, k, 0x14, 0x13]
+        return prog, (lambda o, ops, lf=lf, k=k: o.run("mul_shoup", lf(o, ops), ops[k], o.run("compute_shoup", ops[k]))), max(ld, 3)
+    rp, rf, rd = _random_tree(rng, nops, depth - 1)
+    tok = {"add": 0x10, "sub": 0x11, "mul": 0x12}[kind]
+    return lp + rp + [tok], (lambda o, ops, lf=lf, rf=rf, kind=kind: o.run(kind, lf(o, ops), rf(o, ops))), max(ld, rd + 1)
+
+
+def test_fused_expression_evaluator_random_trees():
+    """nflgpu_eval (the reference's expression templates, ops.hpp:52-97 + core.hpp:24-37): random expression trees over
+    up to 8 operands in ONE kernel, compared with the oracle evaluating the same tree one functor at a time."""
+    import random
+    rng = random.Random(7)
+    for bits, N, M in ((64, 1024, 4), (32, 4096, 3), (16, 512, 2)):
+        c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+        batch = 6
+        ops_host = [random_polys(bits, N, M, batch, 900 + i) for i in range(8)]
+        dev = []
+        for h in ops_host:
+            p = c.alloc(batch)
+            c.upload(p, h, batch)
+            dev.append(p)
+        out = c.alloc(batch)
+        done = 0
+        while done < 20:
+            nops = rng.randint(1, 8)
+            prog, fn, depth = _random_tree(rng, nops, rng.randint(1, 4))
+            if len(prog) > 32 or depth > 8:
+                continue
+            if done % 5 == 4:  # root compute_shoup (its result is a Shoup word, not a residue, so only at the root)
+                prog, fn = prog + [0x14], (lambda o_, ops, fn=fn: o_.run("compute_shoup", fn(o_, ops)))
+            c.eval(out, dev[:nops], prog, batch)
+            got = np.empty_like(ops_host[0])
+            c.download(got, out, batch)
+            c.sync()
+            assert np.array_equal(got, fn(o, ops_host)), (bits, prog)
+            done += 1
+        c.eval(dev[0], dev[:2], [0, 1, 0x12, 0, 0x10], batch)   # dst aliases an operand: a*b + a, in place
+        got = np.empty_like(ops_host[0])
+        c.download(got, dev[0], batch)
+        c.sync()
+        assert np.array_equal(got, o.run("muladd", ops_host[0], ops_host[0], ops_host[1]))
+        with pytest.raises(nb.NflGpuError):
+            c.eval(out, dev[:2], [0, 1], batch)          # leaves two values
+        with pytest.raises(nb.NflGpuError):
+            c.eval(out, dev[:2], [0, 0x10], batch)       # stack underflow
+        with pytest.raises(nb.NflGpuError):
+            c.eval(out, dev[:2], [5], batch)             # operand out of range
+        for p in dev + [out]:
+            c.free(p)

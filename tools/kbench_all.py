@@ -30,10 +30,12 @@ for name, bits, N, M, batch in CONFIGS:
            "inv": (lambda i: ctx.ntt_inv(d[i].data_ptr(), a[i].data_ptr(), batch, s), 2),
            "mul": (lambda i: ctx.mul(d[i].data_ptr(), a[i].data_ptr(), b[i].data_ptr(), batch, s), 3),
            "add": (lambda i: ctx.add(d[i].data_ptr(), a[i].data_ptr(), b[i].data_ptr(), batch, s), 3),
+           "muladd": (lambda i: ctx.muladd(d[i].data_ptr(), a[i].data_ptr(), b[i].data_ptr(), a[(i + 1) % R].data_ptr(), batch, s), 4),
+           "eval(a+b*c)": (lambda i: ctx.eval(d[i].data_ptr(), [a[i].data_ptr(), b[i].data_ptr(), a[(i + 1) % R].data_ptr()], [0, 1, 2, 0x12, 0x10], batch, s), 4),
            "polymul": (lambda i: ctx.polymul(d[i].data_ptr(), a[i].data_ptr(), b[i].data_ptr(), batch, s), 3)}
     line = f"{name:8s} u{bits} N={N:5d} M={M:2d} batch={batch:5d} ({nbytes >> 20:5d} MiB) "
     for op, (fn, passes) in ops.items():
-        for i in range(2):
+        for i in range(3):
             fn(i % R)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
