@@ -126,39 +126,10 @@ template <int LB> static cudaError_t launch_limb(int op, const PwArgs &a, int nu
 // driven by core.hpp:24-37).  Here the tree arrives as a postfix program that every thread interprets on a small
 // value stack; the program is uniform across the grid, so the interpreter's branches never diverge and the kernel
 // stays HBM-bound: each operand is read exactly once and the result written once, whatever the tree.
-// One interpreter step at a statically known stack depth D: every stack access below has a compile-time index, so
-// the value stack lives in registers (a runtime-indexed stack would be spilled to local memory: measured 1.8x slower).
-template <int LB, int D> struct EvStep {
-  typedef typename PW<LB>::Word Word;
-  typedef typename PW<LB>::Store Store;
-  static constexpr int VEC = PW<LB>::VEC;
-  static __device__ __forceinline__ void run(Word (&st)[EV_MAX_STACK][VEC], uint32_t tok, const EvArgs &a, size_t at, Word p, uint64_t kc) {
-    if (tok < EV_MAX_OPERANDS) {
-      if constexpr (D < EV_MAX_STACK) VecIO<LB>::load(st[D], reinterpret_cast<const Store *>(a.operands[tok]) + at);
-    } else if (tok == EV_COMPUTE_SHOUP) {
-      if constexpr (D >= 1) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) st[D - 1][i] = Functor<LB, PW_COMPUTE_SHOUP>::apply(st[D - 1][i], 0, 0, 0, p, kc);
-      }
-    } else if (tok == EV_MUL_SHOUP) {
-      if constexpr (D >= 3) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) st[D - 3][i] = Functor<LB, PW_MUL_SHOUP>::apply(st[D - 3][i], st[D - 2][i], st[D - 1][i], 0, p, kc);
-      }
-    } else {
-      if constexpr (D >= 2) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const Word x = st[D - 2][i], y = st[D - 1][i];
-          st[D - 2][i] = tok == EV_ADD ? Functor<LB, PW_ADD>::apply(x, y, 0, 0, p, kc)
-                       : tok == EV_SUB ? Functor<LB, PW_SUB>::apply(x, y, 0, 0, p, kc)
-                                       : Functor<LB, PW_MUL>::apply(x, y, 0, 0, p, kc);
-        }
-      }
-    }
-  }
-};
-
+// All operand vectors of a thread are fetched up front (independent loads in flight together; fetching each one only
+// when its token is reached serialises the HBM latencies).  The small operand file and value stack are indexed by
+// program-dependent values, so the compiler keeps them in (L1-resident) local memory; a variant with a register-
+// resident stack dispatched on the stack depth was measured slower (more registers -> fewer resident warps).
 template <int LB>
 __global__ void __launch_bounds__(256) eval_kernel(const EvArgs a) {
   typedef typename PW<LB>::Word Word;
@@ -173,22 +144,35 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvArgs a) {
   for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = v >> row_shift, off = v & (vec_per_row - 1);
     const size_t at = ((size_t)b * a.nmoduli + cm) * a.degree + off * VEC;
+    Word opv[EV_MAX_OPERANDS][VEC];
+#pragma unroll
+    for (int k = 0; k < EV_MAX_OPERANDS; ++k)
+      if (a.operands[k] != nullptr) VecIO<LB>::load(opv[k], reinterpret_cast<const Store *>(a.operands[k]) + at);
     Word st[EV_MAX_STACK][VEC];
-    int sp = 0;  // uniform across the grid: the switch below never diverges
+    int sp = 0;
     for (uint32_t t = 0; t < a.ntokens; ++t) {
       const uint32_t tok = a.program[t];
-      switch (sp) {
-        case 0: EvStep<LB, 0>::run(st, tok, a, at, p, kc); break;
-        case 1: EvStep<LB, 1>::run(st, tok, a, at, p, kc); break;
-        case 2: EvStep<LB, 2>::run(st, tok, a, at, p, kc); break;
-        case 3: EvStep<LB, 3>::run(st, tok, a, at, p, kc); break;
-        case 4: EvStep<LB, 4>::run(st, tok, a, at, p, kc); break;
-        case 5: EvStep<LB, 5>::run(st, tok, a, at, p, kc); break;
-        case 6: EvStep<LB, 6>::run(st, tok, a, at, p, kc); break;
-        case 7: EvStep<LB, 7>::run(st, tok, a, at, p, kc); break;
-        default: EvStep<LB, 8>::run(st, tok, a, at, p, kc); break;
+      if (tok < EV_MAX_OPERANDS) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) st[sp][i] = opv[tok][i];
+        ++sp;
+      } else if (tok == EV_COMPUTE_SHOUP) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) st[sp - 1][i] = Functor<LB, PW_COMPUTE_SHOUP>::apply(st[sp - 1][i], 0, 0, 0, p, kc);
+      } else if (tok == EV_MUL_SHOUP) {
+        sp -= 2;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) st[sp - 1][i] = Functor<LB, PW_MUL_SHOUP>::apply(st[sp - 1][i], st[sp][i], st[sp + 1][i], 0, p, kc);
+      } else {
+        --sp;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const Word x = st[sp - 1][i], y = st[sp][i];
+          st[sp - 1][i] = tok == EV_ADD ? Functor<LB, PW_ADD>::apply(x, y, 0, 0, p, kc)
+                        : tok == EV_SUB ? Functor<LB, PW_SUB>::apply(x, y, 0, 0, p, kc)
+                                        : Functor<LB, PW_MUL>::apply(x, y, 0, 0, p, kc);
+        }
       }
-      sp += tok < EV_MAX_OPERANDS ? 1 : tok == EV_COMPUTE_SHOUP ? 0 : tok == EV_MUL_SHOUP ? -2 : -1;
     }
     VecIO<LB>::store(dst + at, st[0]);
   }
