@@ -278,7 +278,6 @@ def run_b200(args):
     t_end.record(stream)
     barrier()
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
     ms = t_begin.elapsed_time(t_end)
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     inv_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
@@ -308,6 +307,7 @@ def run_b200(args):
         e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None  # sampled across both timed regions (device-resident + end-to-end)
     if dist is not None:
         t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
