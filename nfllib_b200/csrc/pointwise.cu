@@ -126,10 +126,12 @@ template <int LB> static cudaError_t launch_limb(int op, const PwArgs &a, int nu
 // driven by core.hpp:24-37).  Here the tree arrives as a postfix program that every thread interprets on a small
 // value stack; the program is uniform across the grid, so the interpreter's branches never diverge and the kernel
 // stays HBM-bound: each operand is read exactly once and the result written once, whatever the tree.
-// All operand vectors of a thread are fetched up front (independent loads in flight together; fetching each one only
-// when its token is reached serialises the HBM latencies).  The small operand file and value stack are indexed by
-// program-dependent values, so the compiler keeps them in (L1-resident) local memory; a variant with a register-
-// resident stack dispatched on the stack depth was measured slower (more registers -> fewer resident warps).
+// The operand file and value stack are indexed by program-dependent values, so the compiler keeps the stack in
+// (L1-resident) local memory at 32 registers per thread = full occupancy, which hides the operand loads.  Measured on
+// B200 for `a + b*c` over 128 MiB operands (tools/kbench_all.py): 166 us, against 91 us for the specialised muladd kernel
+// and 149 us for two separate kernels; variants with a register-resident stack (static-depth dispatch) or with all
+// operands prefetched were slower (205 / 216 us: more registers, fewer resident warps).  The interpreter's value is one
+// launch and no temporaries for arbitrary trees; the shapes the reference names keep their specialised kernels.
 template <int LB>
 __global__ void __launch_bounds__(256) eval_kernel(const EvArgs a) {
   typedef typename PW<LB>::Word Word;
@@ -144,17 +146,12 @@ __global__ void __launch_bounds__(256) eval_kernel(const EvArgs a) {
   for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = v >> row_shift, off = v & (vec_per_row - 1);
     const size_t at = ((size_t)b * a.nmoduli + cm) * a.degree + off * VEC;
-    Word opv[EV_MAX_OPERANDS][VEC];
-#pragma unroll
-    for (int k = 0; k < EV_MAX_OPERANDS; ++k)
-      if (a.operands[k] != nullptr) VecIO<LB>::load(opv[k], reinterpret_cast<const Store *>(a.operands[k]) + at);
     Word st[EV_MAX_STACK][VEC];
     int sp = 0;
     for (uint32_t t = 0; t < a.ntokens; ++t) {
       const uint32_t tok = a.program[t];
       if (tok < EV_MAX_OPERANDS) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) st[sp][i] = opv[tok][i];
+        VecIO<LB>::load(st[sp], reinterpret_cast<const Store *>(a.operands[tok]) + at);
         ++sp;
       } else if (tok == EV_COMPUTE_SHOUP) {
 #pragma unroll
