@@ -69,7 +69,9 @@ struct nflgpu_ctx {
   std::atomic<uint64_t> launches{0};
   static constexpr int kStages = 4;
   HostStage stage[kStages];
-  size_t stage_polys = 0;
+  size_t stage_polys = 0;  // capacity of every staging buffer, in polynomials
+  // The host-buffer pipeline below uses per-context staging state: concurrent nflgpu_host_op calls on ONE context
+  // must be serialised by the caller (distinct contexts are independent).
 };
 
 namespace {
@@ -478,7 +480,7 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   size_t chunk = chunk_bytes / poly_bytes;
   if (chunk == 0) chunk = 1;
   if (chunk > batch) chunk = batch;
-  if (ctx->stage_polys != chunk) {
+  if (ctx->stage_polys < chunk) {  // staging buffers only ever grow (capacity = largest chunk seen so far)
     for (auto &s : ctx->stage) {
       if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       for (int i = 0; i < 4; ++i) {
