@@ -564,6 +564,9 @@ public:
 
   void ntt_pow_phi() { detail::check(nflgpu_ntt_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_fwd"); }
   void invntt_pow_invphi() { detail::check(nflgpu_ntt_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_inv"); }
+  // the cyclic transforms underneath (poly::core::ntt / inv_ntt, core.hpp:455-557; what tests/ntt_perfs.cpp times)
+  void core_ntt() { detail::check(nflgpu_ntt_raw_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_fwd"); }
+  void core_inv_ntt() { detail::check(nflgpu_ntt_raw_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_inv"); }
 
 #define NFLB200_BATCH_BIN(NAME, CALL)                                                                                       \
   void NAME(batch const &a, batch const &b) {                                                                               \

@@ -95,6 +95,14 @@ int nflgpu_ntt_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, vo
  * nflgpu_ntt_fwd (bit-reversed input order, natural output order, canonical).  dst may equal src. */
 int nflgpu_ntt_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream);
 
+/* The cyclic transform underneath, without the phi twist: poly::core::ntt(x, wtab, winvtab, p) (core.hpp:455-532; the
+ * function tests/ntt_perfs.cpp:122-134,165-171 times through its friend proxy) on every residue:
+ * dst[b][cm][j] = sum_i src[b][cm][i] * omega_cm^(i*bitrev(j)) mod p_cm, canonical.  Tables are built on first use. */
+int nflgpu_ntt_raw_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream);
+/* poly::core::inv_ntt (core.hpp:539-557: bit-reverse, core::ntt with omega^-1, bit-reverse): the unscaled inverse,
+ * nflgpu_ntt_raw_inv(nflgpu_ntt_raw_fwd(x)) = degree * x mod p (the reference folds N^-1 into the twist that follows). */
+int nflgpu_ntt_raw_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream);
+
 /* ---- pointwise functors (the expression evaluator core.hpp:24-37 applied to one functor) ---------------- */
 
 /* operator*  = ops::mulmod        (ops.hpp:184-219) */

@@ -47,7 +47,7 @@ def lib():
         L.nflgpu_upload.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_download.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_sync.argtypes = [vp, vp]
-        for name in ("nflgpu_ntt_fwd", "nflgpu_ntt_inv", "nflgpu_compute_shoup"):
+        for name in ("nflgpu_ntt_fwd", "nflgpu_ntt_inv", "nflgpu_compute_shoup", "nflgpu_ntt_raw_fwd", "nflgpu_ntt_raw_inv"):
             getattr(L, name).argtypes = [vp, vp, vp, sz, vp]
         for name in ("nflgpu_mul", "nflgpu_add", "nflgpu_sub", "nflgpu_polymul"):
             getattr(L, name).argtypes = [vp, vp, vp, vp, sz, vp]
@@ -132,6 +132,12 @@ class Context:
 
     def ntt_inv(self, dst, src, batch, stream=0):
         _check(lib().nflgpu_ntt_inv(self.h, dst, src, batch, stream))
+
+    def ntt_raw_fwd(self, dst, src, batch, stream=0):
+        _check(lib().nflgpu_ntt_raw_fwd(self.h, dst, src, batch, stream))
+
+    def ntt_raw_inv(self, dst, src, batch, stream=0):
+        _check(lib().nflgpu_ntt_raw_inv(self.h, dst, src, batch, stream))
 
     def mul(self, dst, a, b, batch, stream=0):
         _check(lib().nflgpu_mul(self.h, dst, a, b, batch, stream))

@@ -66,6 +66,9 @@ struct nflgpu_ctx {
   uint64_t *d_moduli64 = nullptr;   // uint64_t[nmoduli] for the pointwise kernels
   uint64_t *d_consts = nullptr;     // Barrett constants, pointwise.h
   void *d_tw_fwd = nullptr, *d_tw_inv = nullptr;
+  void *d_tw_raw_fwd = nullptr, *d_tw_raw_inv = nullptr;  // cyclic (no-twist) tables, built on first use
+  std::vector<uint64_t> roots;
+  uint64_t kmax = 0;
   std::atomic<uint64_t> launches{0};
   static constexpr int kStages = 4;
   HostStage stage[kStages];
@@ -75,6 +78,36 @@ struct nflgpu_ctx {
 };
 
 namespace {
+
+// builds the twiddle tables of all residues (tables.cpp), narrows them to the kernel word type and uploads them
+int upload_tables(nflgpu_ctx *ctx, bool raw, void **d_fwd, void **d_inv) {
+  const int word_bits = ctx->limb_bits == 64 ? 64 : 32;
+  const size_t tw_entry = ctx->limb_bits == 64 ? 16 : 8, degree = ctx->degree, nmoduli = ctx->nmoduli;
+  std::vector<unsigned char> hf(nmoduli * degree * tw_entry), hi(nmoduli * degree * tw_entry);
+  for (size_t cm = 0; cm < nmoduli; ++cm) {
+    ResidueTables t;
+    build_residue_tables(ctx->limb_bits, word_bits, degree, ctx->moduli[cm], ctx->roots[cm], ctx->kmax, &t, raw);
+    for (size_t i = 0; i < degree; ++i) {
+      if (word_bits == 64) {
+        uint64_t *f = reinterpret_cast<uint64_t *>(hf.data()) + (cm * degree + i) * 2;
+        uint64_t *v = reinterpret_cast<uint64_t *>(hi.data()) + (cm * degree + i) * 2;
+        f[0] = t.fwd_w[i]; f[1] = t.fwd_ws[i]; v[0] = t.inv_w[i]; v[1] = t.inv_ws[i];
+      } else {
+        uint32_t *f = reinterpret_cast<uint32_t *>(hf.data()) + (cm * degree + i) * 2;
+        uint32_t *v = reinterpret_cast<uint32_t *>(hi.data()) + (cm * degree + i) * 2;
+        f[0] = (uint32_t)t.fwd_w[i]; f[1] = (uint32_t)t.fwd_ws[i]; v[0] = (uint32_t)t.inv_w[i]; v[1] = (uint32_t)t.inv_ws[i];
+      }
+    }
+  }
+  cudaError_t e;
+  if ((e = cudaMalloc(d_fwd, hf.size())) != cudaSuccess || (e = cudaMalloc(d_inv, hi.size())) != cudaSuccess ||
+      (e = cudaMemcpy(*d_fwd, hf.data(), hf.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(*d_inv, hi.data(), hi.size(), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    set_error(std::string("twiddle table upload: ") + cudaGetErrorName(e));
+    return NFLGPU_ERR_CUDA;
+  }
+  return NFLGPU_OK;
+}
 
 struct DeviceGuard {
   int prev = -1;
@@ -93,7 +126,8 @@ int check_buf(const nflgpu_ctx *ctx, const void *p, const char *name) {
   return NFLGPU_OK;
 }
 
-int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch, void *stream, const void *other = nullptr) {
+int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch, void *stream, const void *other = nullptr,
+            bool raw = false) {
   int rc;
   if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, src, "src"))) return rc;
   if (mode == 2 && (rc = check_buf(ctx, other, "other"))) return rc;
@@ -101,8 +135,13 @@ int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch,
   if (batch == 0) return NFLGPU_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  if (raw && !ctx->d_tw_raw_fwd) {  // first use of the cyclic transform on this context
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (int rc2 = upload_tables(ctx, true, &ctx->d_tw_raw_fwd, &ctx->d_tw_raw_inv)) return rc2;
+  }
   NttLaunch l;
-  l.src = src; l.dst = dst; l.tw = mode == 1 ? ctx->d_tw_inv : ctx->d_tw_fwd; l.moduli = ctx->d_moduli_word;
+  l.src = src; l.dst = dst; l.moduli = ctx->d_moduli_word;
+  l.tw = raw ? (mode == 1 ? ctx->d_tw_raw_inv : ctx->d_tw_raw_fwd) : (mode == 1 ? ctx->d_tw_inv : ctx->d_tw_fwd);
   l.nmoduli = (uint32_t)ctx->nmoduli; l.batch = (uint32_t)batch;
   l.other = other; l.consts = ctx->d_consts;
   CUDA_TRY(launch_ntt(ctx->limb_bits, ctx->log2_degree, mode, l, ctx->device, ctx->num_sms, (cudaStream_t)stream));
@@ -209,26 +248,12 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
   if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; set_error("cannot query CUDA device"); return NFLGPU_ERR_CUDA; }
   ctx->num_sms = prop.multiProcessorCount;
 
-  // tables (tables.cpp), narrowed to the kernel word type: 64-bit limbs -> {u64,u64}; 32/16-bit -> {u32,u32}
+  ctx->roots = rts;
+  ctx->kmax = lim.kMaxPolyDegree;
   const int word_bits = limb_bits == 64 ? 64 : 32;
-  const size_t tw_entry = limb_bits == 64 ? 16 : 8;
-  std::vector<unsigned char> hf(nmoduli * degree * tw_entry), hi(nmoduli * degree * tw_entry);
   std::vector<uint64_t> consts(nmoduli);
   std::vector<unsigned char> words(nmoduli * (word_bits / 8));
   for (size_t cm = 0; cm < nmoduli; ++cm) {
-    ResidueTables t;
-    build_residue_tables(limb_bits, word_bits, degree, ctx->moduli[cm], rts[cm], lim.kMaxPolyDegree, &t);
-    for (size_t i = 0; i < degree; ++i) {
-      if (word_bits == 64) {
-        uint64_t *f = reinterpret_cast<uint64_t *>(hf.data()) + (cm * degree + i) * 2;
-        uint64_t *v = reinterpret_cast<uint64_t *>(hi.data()) + (cm * degree + i) * 2;
-        f[0] = t.fwd_w[i]; f[1] = t.fwd_ws[i]; v[0] = t.inv_w[i]; v[1] = t.inv_ws[i];
-      } else {
-        uint32_t *f = reinterpret_cast<uint32_t *>(hf.data()) + (cm * degree + i) * 2;
-        uint32_t *v = reinterpret_cast<uint32_t *>(hi.data()) + (cm * degree + i) * 2;
-        f[0] = (uint32_t)t.fwd_w[i]; f[1] = (uint32_t)t.fwd_ws[i]; v[0] = (uint32_t)t.inv_w[i]; v[1] = (uint32_t)t.inv_ws[i];
-      }
-    }
     const uint64_t p = ctx->moduli[cm];
     if (limb_bits == 64) { consts[cm] = newton_pn(64, p); reinterpret_cast<uint64_t *>(words.data())[cm] = p; }
     else {
@@ -236,6 +261,7 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
       reinterpret_cast<uint32_t *>(words.data())[cm] = (uint32_t)p;
     }
   }
+  if (int rc = upload_tables(ctx, false, &ctx->d_tw_fwd, &ctx->d_tw_inv)) { nflgpu_ctx_destroy(ctx); return rc; }
 #define CTX_TRY(expr)                                                                         \
   do {                                                                                        \
     cudaError_t e_ = (expr);                                                                  \
@@ -245,13 +271,9 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
       return NFLGPU_ERR_CUDA;                                                                 \
     }                                                                                         \
   } while (0)
-  CTX_TRY(cudaMalloc(&ctx->d_tw_fwd, hf.size()));
-  CTX_TRY(cudaMalloc(&ctx->d_tw_inv, hi.size()));
   CTX_TRY(cudaMalloc(&ctx->d_moduli_word, words.size()));
   CTX_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->d_moduli64), nmoduli * 8));
   CTX_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->d_consts), nmoduli * 8));
-  CTX_TRY(cudaMemcpy(ctx->d_tw_fwd, hf.data(), hf.size(), cudaMemcpyHostToDevice));
-  CTX_TRY(cudaMemcpy(ctx->d_tw_inv, hi.data(), hi.size(), cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_moduli_word, words.data(), words.size(), cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_moduli64, ctx->moduli.data(), nmoduli * 8, cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_consts, consts.data(), nmoduli * 8, cudaMemcpyHostToDevice));
@@ -268,7 +290,7 @@ int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
     for (int i = 0; i < 4; ++i) { if (s.dev[i]) cudaFree(s.dev[i]); if (s.pin[i]) cudaFreeHost(s.pin[i]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
+  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
   delete ctx;
   return NFLGPU_OK;
 }
@@ -330,6 +352,13 @@ int nflgpu_sync(nflgpu_ctx *ctx, void *stream) {
 
 int nflgpu_ntt_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, 0, dst, src, batch, stream); }
 int nflgpu_ntt_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) { return run_ntt(ctx, 1, dst, src, batch, stream); }
+
+int nflgpu_ntt_raw_fwd(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) {
+  return run_ntt(ctx, 0, dst, src, batch, stream, nullptr, true);
+}
+int nflgpu_ntt_raw_inv(nflgpu_ctx *ctx, void *dst, const void *src, size_t batch, void *stream) {
+  return run_ntt(ctx, 1, dst, src, batch, stream, nullptr, true);
+}
 
 int nflgpu_mul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
   return run_pw(ctx, PW_MUL, 2, dst, a, b, nullptr, nullptr, batch, stream);

@@ -28,8 +28,9 @@ struct ResidueTables {
   std::vector<uint64_t> inv_w, inv_ws;  // N entries each; [N-1] = N^-1, entry of stage 0 pre-multiplied by N^-1
 };
 // limb_bits: 16/32/64 (Shoup shift); word_bits: 32 or 64 (kernel word: 16-bit limbs compute in 32-bit words)
+// raw = true builds the tables of the cyclic transform core::ntt / core::inv_ntt (no phi twist, no N^-1)
 void build_residue_tables(int limb_bits, int word_bits, size_t N, uint64_t p, uint64_t root, uint64_t kmax,
-                          ResidueTables *out);
+                          ResidueTables *out, bool raw = false);
 
 void set_error(const std::string &msg);
 

@@ -25,7 +25,7 @@ static inline size_t bitrev(size_t v, int bits) {
 }
 
 void build_residue_tables(int limb_bits, int word_bits, size_t N, uint64_t p, uint64_t root, uint64_t kmax,
-                          ResidueTables *out) {
+                          ResidueTables *out, bool raw) {
   int n = 0;
   while (((size_t)1 << n) < N) ++n;
   // core.hpp:640-645: psi = root^(kmax / N) by repeated squaring; a primitive 2N-th root of unity
@@ -49,16 +49,20 @@ void build_residue_tables(int limb_bits, int word_bits, size_t N, uint64_t p, ui
         for (size_t g = 0; g < G; ++g) {
           size_t e_idx = ((size_t)1 << q) - 1 + kk;
           size_t k = ((size_t)1 << (s0 + q)) + (g << q) + kk;  // index into the bit-reversed power table
-          size_t ex = bitrev(k, n);
+          // merged (negacyclic) tables: psi^bitrev_n(k) = psi^(t + 2t*bitrev_s(i)), t = N/2^(s+1), i = group index;
+          // raw (cyclic, core::ntt / core::inv_ntt without the phi twist): the same without the psi^t factor
+          size_t ex = raw ? (bitrev(k, n) - ((size_t)1 << (n - 1 - (s0 + q)))) : bitrev(k, n);
           size_t at = off + e_idx * G + g;
           uint64_t w = pw[ex], iw = ipw[ex];
-          if (k == 1) iw = mm(iw, ninv, p);  // last inverse stage also scales by N^-1
+          if (k == 1 && !raw) iw = mm(iw, ninv, p);  // last inverse stage also scales by N^-1
           out->fwd_w[at] = w; out->fwd_ws[at] = shoup_of(w, p, limb_bits);
           out->inv_w[at] = iw; out->inv_ws[at] = shoup_of(iw, p, limb_bits);
         }
   }
-  out->inv_w[N - 1] = ninv;
-  out->inv_ws[N - 1] = shoup_of(ninv, p, limb_bits);
+  // slot N-1: the factor applied to the (U+V) output of the last inverse stage: N^-1, or 1 for the raw transform
+  // (core::inv_ntt leaves the scaling to the twist that follows it, core.hpp:539-557,613)
+  out->inv_w[N - 1] = raw ? 1 : ninv;
+  out->inv_ws[N - 1] = shoup_of(raw ? 1 : ninv, p, limb_bits);
 }
 
 }  // namespace nflgpu

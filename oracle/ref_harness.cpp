@@ -12,7 +12,7 @@
 //   mul/add/sub-> operator* / + / -                   include/nfl/poly.hpp:346-350
 //   mul_shoup  -> nfl::shoup(a * b, bprime)           include/nfl/ops.hpp:266-277
 //   compute_shoup -> nfl::compute_shoup(a)            include/nfl/poly.hpp:352
-//   raw_ntt    -> poly::core::ntt via the friend proxy, as tests/ntt_perfs.cpp:122-134 does
+//   raw_ntt / raw_intt -> poly::core::ntt / inv_ntt via the friend proxy, as tests/ntt_perfs.cpp:122-134 does
 //   polymul    -> fwd(a), fwd(b), a*b, inv            (tests/nfllib_demo_main_op.cpp:31-45 pattern)
 #include <cstdint>
 #include <cstdlib>
@@ -29,13 +29,16 @@ public:
   static void raw_ntt(P &p, size_t cm) {
     P::core::ntt(&p(cm, 0), p.base.omegas[cm], p.base.shoupomegas[cm], P::get_modulus(cm));
   }
+  static void raw_inv_ntt(P &p, size_t cm) {  // core.hpp:539-557, reached the same way
+    P::core::inv_ntt(&p(cm, 0), p.base.invomegas[cm], p.base.shoupinvomegas[cm], p.base.invpolyDegree[cm], P::get_modulus(cm));
+  }
 };
 }}
 
 namespace {
 
 enum Op { OP_FWD = 0, OP_INV, OP_MUL, OP_MUL_SHOUP, OP_COMPUTE_SHOUP, OP_ADD, OP_SUB, OP_RAW_NTT, OP_POLYMUL,
-          OP_MULADD /* out = a + b*c, expression-fused */ };
+          OP_MULADD /* out = a + b*c, expression-fused */, OP_RAW_INTT };
 
 template <class P>
 void *aligned_polys(size_t n) {
@@ -60,6 +63,10 @@ void run_range(int op, P *out, const P *a, const P *b, const P *c, size_t lo, si
       case OP_RAW_NTT:
         if (out != a) std::memcpy(&out[i], &a[i], sizeof(P));
         for (size_t cm = 0; cm < P::nmoduli; ++cm) nfl::tests::poly_tests_proxy<P>::raw_ntt(out[i], cm);
+        break;
+      case OP_RAW_INTT:
+        if (out != a) std::memcpy(&out[i], &a[i], sizeof(P));
+        for (size_t cm = 0; cm < P::nmoduli; ++cm) nfl::tests::poly_tests_proxy<P>::raw_inv_ntt(out[i], cm);
         break;
       case OP_POLYMUL: {
         P *ta = static_cast<P *>(aligned_polys<P>(2));

@@ -135,6 +135,14 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
     t.assign_add(da, da); t.assign_sub(t, da);                 // t = a
     t.ntt_pow_phi(); dump(t);                                  // fwd(a)
     t.invntt_pow_invphi(); dump(t);                            // a again
+    t.core_ntt(); t.core_inv_ntt();                            // = N * a  (core::inv_ntt does not scale, core.hpp:539-557)
+    {
+      t.download(h);
+      for (size_t i = 0; i < count; ++i)
+        for (size_t cm = 0; cm < P::nmoduli; ++cm)
+          for (size_t j = 0; j < P::degree; j += 97)
+            REQUIRE(h[i](cm, j) == static_cast<T>((G(a[i](cm, j)) * (P::degree % P::get_modulus(cm))) % P::get_modulus(cm)));
+    }
     t.assign_mul(da, db); dump(t);
     u.assign_compute_shoup(db); t.assign_mul_shoup(da, db, u); dump(t);
     t.assign_muladd(da, db, da);                               // a + b*a

@@ -44,7 +44,7 @@ def main():
         np.savez_compressed(os.path.join(GOLDEN, f"kat_u{bits}_n{N}_m{M}.npz"), a=a, b=b, fwd_a=fa, fwd_b=fb,
                             inv_a=r.run("inv", a), mul=r.run("mul", a, b), add=r.run("add", a, b), sub=r.run("sub", a, b),
                             shoup_b=bs, mul_shoup=r.run("mul_shoup", a, b, bs), polymul=r.run("polymul", a, b),
-                            muladd=r.run("muladd", a, b, fa), raw_ntt=r.run("raw_ntt", a))
+                            muladd=r.run("muladd", a, b, fa), raw_ntt=r.run("raw_ntt", a), raw_intt=r.run("raw_intt", a))
 
     # hashes at the BASELINE.json configurations (batch kept small; inputs are seeded, see random_polys)
     hashes = {}

@@ -12,7 +12,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 DTYPES = {16: np.uint16, 32: np.uint32, 64: np.uint64}
 OPS = {"fwd": 0, "inv": 1, "mul": 2, "mul_shoup": 3, "compute_shoup": 4, "add": 5, "sub": 6, "raw_ntt": 7,
-       "polymul": 8, "muladd": 9}
+       "polymul": 8, "muladd": 9, "raw_intt": 10}
 
 
 def aligned(shape, dtype, align=64):

@@ -48,6 +48,8 @@ def test_reference_fixtures(path):
     assert np.array_equal(c.run_device("ntt_fwd", b, inplace=True), k["fwd_b"])
     assert np.array_equal(c.run_device("ntt_inv", a), k["inv_a"])
     assert np.array_equal(c.run_device("ntt_inv", k["fwd_a"], inplace=True), a)
+    assert np.array_equal(c.run_device("ntt_raw_fwd", a), k["raw_ntt"])      # core::ntt, the tests/ntt_perfs.cpp path
+    assert np.array_equal(c.run_device("ntt_raw_inv", a), k["raw_intt"])     # core::inv_ntt
     assert np.array_equal(c.run_device("mul", a, b), k["mul"])
     assert np.array_equal(c.run_device("add", a, b), k["add"])
     assert np.array_equal(c.run_device("sub", a, b), k["sub"])
@@ -74,6 +76,8 @@ def test_all_sizes_vs_oracle(bits, n):
         assert np.array_equal(c.run_device("ntt_fwd", a), fa), (bits, N, M, "fwd")
         assert np.array_equal(c.run_device("ntt_inv", a), o.run("inv", a)), (bits, N, M, "inv")
         assert np.array_equal(c.run_device("ntt_inv", fa), a), (bits, N, M, "roundtrip")
+        assert np.array_equal(c.run_device("ntt_raw_fwd", a), o.run("raw_ntt", a)), (bits, N, M, "raw fwd")
+        assert np.array_equal(c.run_device("ntt_raw_inv", a), o.run("raw_intt", a)), (bits, N, M, "raw inv")
         assert np.array_equal(c.run_device("mul", a, b), o.run("mul", a, b))
         assert np.array_equal(c.run_device("add", a, b), o.run("add", a, b))
         assert np.array_equal(c.run_device("sub", a, b), o.run("sub", a, b))

@@ -33,6 +33,7 @@ def test_oracle_matches_reference_fixtures(path):
     assert np.array_equal(o.run("fwd", b), k["fwd_b"])
     assert np.array_equal(o.run("inv", a), k["inv_a"])
     assert np.array_equal(o.run("raw_ntt", a), k["raw_ntt"])
+    assert np.array_equal(o.run("raw_intt", a), k["raw_intt"])
     assert np.array_equal(o.run("mul", a, b), k["mul"])
     assert np.array_equal(o.run("add", a, b), k["add"])
     assert np.array_equal(o.run("sub", a, b), k["sub"])
@@ -99,7 +100,7 @@ def test_oracle_matches_live_reference_all_sizes(bits):
         batch = 2 if N >= 8192 else 4
         a = random_polys(bits, N, 1, batch, 100 + ln)
         b = random_polys(bits, N, 1, batch, 200 + ln)
-        for op in ("fwd", "inv", "raw_ntt"):
+        for op in ("fwd", "inv", "raw_ntt", "raw_intt"):
             assert np.array_equal(o.run(op, a), r.run(op, a)), (bits, N, op)
         for op in ("mul", "add", "sub"):
             assert np.array_equal(o.run(op, a, b), r.run(op, a, b)), (bits, N, op)
