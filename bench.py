@@ -94,10 +94,31 @@ def cpu_baseline(target_seconds=12.0):
     for _ in range(reps):
         cpu_pass(kind, eng, a, work, threads)
     dt = time.perf_counter() - t0
-    return {"value": 2.0 * polys * reps / dt, "unit": UNIT, "cores": threads, "kind": kind,
-            "sample": f"{reps} x (ntt_pow_phi + invntt_pow_invphi) over {polys} seeded polys of the same shape, {threads} host threads, "
-                      f"{dt:.1f} s; build: {flags}",
-            "host_cpu": host_cpu()}
+    out = {"value": 2.0 * polys * reps / dt, "unit": UNIT, "cores": threads, "kind": kind,
+           "sample": f"{reps} x (ntt_pow_phi + invntt_pow_invphi) over {polys} seeded polys of the same shape, {threads} host threads, "
+                     f"{dt:.1f} s; build: {flags}",
+           "host_cpu": host_cpu()}
+    out.update(reference_ntt_perfs())
+    return out
+
+
+def reference_ntt_perfs():
+    """The reference's own micro-benchmark, unmodified (tests/ntt_perfs.cpp built into oracle/_ref/ntt_perfs): microseconds per raw
+    core::ntt of ONE residue (N=1024, uint64), one thread — the number BASELINE.json's '10x ntt_perfs' target refers to."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ntt_perfs")
+    if not os.path.exists(exe):
+        return {}
+    try:
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        return {}
+    res = {}
+    for line in txt.splitlines():
+        if "Time per NTT (lib)" in line:
+            res["ntt_perfs_lib_us_per_residue_ntt"] = float(line.split(":")[1].split()[0])
+        if "Time per NTT (org)" in line:
+            res["ntt_perfs_org_us_per_residue_ntt"] = float(line.split(":")[1].split()[0])
+    return res
 
 
 def usable_cpus():
