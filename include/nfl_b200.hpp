@@ -564,6 +564,11 @@ public:
 
   void ntt_pow_phi() { detail::check(nflgpu_ntt_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_fwd"); }
   void invntt_pow_invphi() { detail::check(nflgpu_ntt_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_inv"); }
+  // count successive poly::set(nfl::uniform()) draws, generated in HBM from the Salsa20 stream (key, first_nonce + i):
+  // bit-identical to the reference's draws under the same key (core.hpp:150-187, lib/prng/fastrandombytes.cpp:21-34)
+  void set_uniform(const uint8_t key[32], uint64_t first_nonce) {
+    detail::check(nflgpu_uniform(ctx(), buf_.p, buf_.count, key, first_nonce, nullptr), "nflgpu_uniform");
+  }
   // the cyclic transforms underneath (poly::core::ntt / inv_ntt, core.hpp:455-557; what tests/ntt_perfs.cpp times)
   void core_ntt() { detail::check(nflgpu_ntt_raw_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_fwd"); }
   void core_inv_ntt() { detail::check(nflgpu_ntt_raw_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_inv"); }

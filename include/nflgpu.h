@@ -142,6 +142,15 @@ int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t 
  * tests/nfllib_demo_main_op.cpp:31-45 — i.e. a*b mod (X^N + 1, p_cm), coefficient domain in and out. */
 int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream);
 
+/* ---- sampler on the input side of the path --------------------------------------------------------------- */
+
+/* `batch` successive poly::set(nfl::uniform()) draws (core.hpp:150-187) written straight into a device batch: polynomial
+ * i is filled from the Salsa20/20 keystream (key, nonce = first_nonce + i) that nfl::fastrandombytes
+ * (lib/prng/fastrandombytes.cpp:21-34) would produce for it, every limb masked to its modulus' bit length and reduced
+ * by one conditional subtraction.  With the same 32-byte key the result is bit-identical to the reference's draws; the
+ * caller owns key management (the reference keys itself once from /dev/urandom). */
+int nflgpu_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, const uint8_t key[32], uint64_t first_nonce, void *stream);
+
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked
  * and double-buffered over two streams.  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,

@@ -55,6 +55,7 @@ def lib():
             getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_muladd_shoup.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_host_op.argtypes = [vp, ci, vp, vp, vp, vp, sz]
+        L.nflgpu_uniform.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_eval.argtypes = [vp, vp, ctypes.POINTER(vp), sz, ctypes.c_char_p, sz, sz, vp]
         _lib = L
     return _lib
@@ -159,6 +160,10 @@ class Context:
 
     def muladd_shoup(self, dst, a, b, c, cprime, batch, stream=0):
         _check(lib().nflgpu_muladd_shoup(self.h, dst, a, b, c, cprime, batch, stream))
+
+    def uniform(self, dst, batch, key, first_nonce, stream=0):
+        """nflgpu_uniform: `batch` poly::set(uniform) draws from the Salsa20 stream (key, first_nonce + i)."""
+        _check(lib().nflgpu_uniform(self.h, dst, batch, bytes(key), first_nonce, stream))
 
     def eval(self, dst, operands, program, batch, stream=0):
         """nflgpu_eval: `operands` = list of device pointers, `program` = postfix bytes (see include/nflgpu.h)."""

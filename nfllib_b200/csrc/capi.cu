@@ -425,6 +425,28 @@ int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t 
   return NFLGPU_OK;
 }
 
+int nflgpu_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst, "dst"))) return rc;
+  if (!key) { set_error("null key"); return NFLGPU_ERR_ARG; }
+  if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  SampleArgs a;
+  a.dst = dst; a.moduli = ctx->d_moduli64;
+  for (int i = 0; i < 8; ++i)
+    a.key[i] = (uint32_t)key[4 * i] | ((uint32_t)key[4 * i + 1] << 8) | ((uint32_t)key[4 * i + 2] << 16) | ((uint32_t)key[4 * i + 3] << 24);
+  a.first_nonce = first_nonce;
+  a.poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
+  a.blocks_per_poly = (a.poly_bytes + 63) / 64;
+  a.nmoduli = (uint32_t)ctx->nmoduli; a.log2_degree = (uint32_t)ctx->log2_degree; a.limb_bits = (uint32_t)ctx->limb_bits;
+  a.batch = (uint32_t)batch;
+  CUDA_TRY(launch_uniform(a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return NFLGPU_OK;
+}
+
 int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {
   int rc;
   if ((rc = check_buf(ctx, dst, "dst")) || (rc = check_buf(ctx, a, "a")) || (rc = check_buf(ctx, b, "b"))) return rc;

@@ -31,5 +31,16 @@ struct EvArgs {
 };
 cudaError_t launch_eval(int limb_bits, const EvArgs &a, int num_sms, cudaStream_t stream);
 
+// On-device uniform sampler (sampler.cu).
+struct SampleArgs {
+  void *dst;
+  const uint64_t *moduli;  // [nmoduli], widened
+  uint32_t key[8];         // Salsa20 key, little-endian words
+  uint64_t first_nonce;
+  uint64_t poly_bytes, blocks_per_poly;  // blocks_per_poly = ceil(poly_bytes / 64)
+  uint32_t nmoduli, log2_degree, limb_bits, batch;
+};
+cudaError_t launch_uniform(const SampleArgs &a, int num_sms, cudaStream_t stream);
+
 }  // namespace nflgpu
 #endif

@@ -131,6 +131,35 @@ int NFLREF_CAT(nflref_run_part, NFLREF_PART)(int op, int limb_bits, size_t degre
 
 #if NFLREF_PART == 0
 
+}  // extern "C"
+// Deterministic stand-in for the reference's entropy source lib/prng/randombytes.cpp (reads /dev/urandom): the Salsa20
+// key that lib/prng/fastrandombytes.cpp:24-27 draws once becomes the fixed bytes 1, 2, ..., 32, which makes the
+// reference's samplers reproducible so that poly::set(uniform) (core.hpp:150-187) can serve as an oracle.  Everything
+// downstream — fastrandombytes.cpp and the Salsa20 assembly — is the reference's own, unmodified code.
+namespace nfl {
+void randombytes(unsigned char *x, unsigned long long xlen) {
+  for (unsigned long long i = 0; i < xlen; ++i) x[i] = (unsigned char)(i + 1);
+}
+}
+static unsigned long long g_uniform_calls = 0;  // mirrors the nonce counter inside fastrandombytes.cpp:17-34
+template <class P> static void uniform_range(P *out, size_t batch) {
+  for (size_t i = 0; i < batch; ++i) { out[i].set(nfl::uniform()); ++g_uniform_calls; }
+}
+#define NFLREF_UNIFORM(T, BITS, N, M) \
+  if (limb_bits == BITS && degree == N && nmoduli == M) { uniform_range(static_cast<nfl::poly<T, N, M> *>(out), batch); return 0; }
+extern "C" {
+
+// out[0..batch) = successive poly::set(nfl::uniform()) draws; *first_nonce receives the 64-bit nonce the first of
+// them used (one fastrandombytes call, i.e. one nonce, per polynomial).  Single-threaded: the reference's PRNG state
+// is a process-global static.
+int nflref_uniform(int limb_bits, size_t degree, size_t nmoduli, void *out, size_t batch, unsigned long long *first_nonce) {
+  if (reinterpret_cast<uintptr_t>(out) & 31) return -2;
+  *first_nonce = g_uniform_calls;
+  NFLREF_UNIFORM(uint64_t, 64, 1024, 4) NFLREF_UNIFORM(uint64_t, 64, 64, 3) NFLREF_UNIFORM(uint32_t, 32, 4096, 1)
+  NFLREF_UNIFORM(uint32_t, 32, 8, 2) NFLREF_UNIFORM(uint16_t, 16, 512, 2) NFLREF_UNIFORM(uint16_t, 16, 16, 1)
+  return -1;
+}
+
 // Tables of the reference, for pinning our own parameter derivation (include/nfl/params.hpp).
 int nflref_params(int limb_bits, size_t count, uint64_t *P, uint64_t *Pn, uint64_t *roots, uint64_t *invkmax,
                   uint64_t *kmax, uint64_t *maxmoduli) {

@@ -46,6 +46,11 @@ def main():
                             shoup_b=bs, mul_shoup=r.run("mul_shoup", a, b, bs), polymul=r.run("polymul", a, b),
                             muladd=r.run("muladd", a, b, fa), raw_ntt=r.run("raw_ntt", a), raw_intt=r.run("raw_intt", a))
 
+    # the reference's own uniform sampler, made reproducible by the harness's fixed Salsa20 key (oracle/ref_harness.cpp)
+    n0, draws = Ref(64, 1024, 4).uniform(2)
+    np.savez_compressed(os.path.join(GOLDEN, "uniform_u64_n1024_m4.npz"), draws=draws, key=np.frombuffer(Ref.FIXED_KEY, dtype=np.uint8),
+                        first_nonce=np.uint64(n0))
+
     # hashes at the BASELINE.json configurations (batch kept small; inputs are seeded, see random_polys)
     hashes = {}
     for name, bits, N, M, batch in [("C1", 64, 1024, 1, 4), ("C2", 64, 1024, 4, 16), ("C3", 64, 16384, 8, 2), ("C4", 32, 4096, 14, 4),

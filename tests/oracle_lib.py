@@ -55,6 +55,7 @@ class Oracle:
             L.nflo_destroy.argtypes = [ctypes.c_void_p]
             L.nflo_run.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_size_t]
             L.nflo_spec_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+            L.nflo_uniform.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64]
             cls._lib = L
         return cls._lib
 
@@ -83,6 +84,12 @@ class Oracle:
         pc = keep[-1].ctypes.data if c is not None else None
         rc = self.lib().nflo_run(self.h, OPS[op], out.ctypes.data, a.ctypes.data, pb, pc, a.size // (self.N * self.M))
         assert rc == 0
+        return out
+
+    def uniform(self, batch, key, first_nonce):
+        """`batch` successive poly::set(uniform) draws from the Salsa20 stream (key, first_nonce + i)."""
+        out = np.empty((batch, self.M, self.N), dtype=self.dtype)
+        self.lib().nflo_uniform(self.h, out.ctypes.data, batch, bytes(key), first_nonce)
         return out
 
     def spec_fwd(self, a):
@@ -127,6 +134,18 @@ class Ref:
                                    a.size // (self.N * self.M), threads)
         assert rc == 0, f"nflref_run rc={rc} for ({self.bits},{self.N},{self.M})"
         return out
+
+    FIXED_KEY = bytes(range(1, 33))  # what the harness's randombytes stub hands to fastrandombytes.cpp
+
+    def uniform(self, batch):
+        """(first_nonce, polys): the reference's own poly::set(uniform) run `batch` times with the fixed key."""
+        out = aligned((batch, self.M, self.N), self.dtype)
+        n = ctypes.c_ulonglong()
+        self.lib().nflref_uniform.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                              ctypes.POINTER(ctypes.c_ulonglong)]
+        rc = self.lib().nflref_uniform(self.bits, self.N, self.M, out.ctypes.data, batch, ctypes.byref(n))
+        assert rc == 0, rc
+        return n.value, out
 
     @classmethod
     def params(cls, bits, count):

@@ -267,3 +267,31 @@ def test_fused_expression_evaluator_random_trees():
             c.eval(out, dev[:2], [5], batch)             # operand out of range
         for p in dev + [out]:
             c.free(p)
+
+
+def test_uniform_sampler_matches_reference_draws():
+    """nflgpu_uniform vs the oracle's restatement of poly::set(uniform) (Salsa20 keystream + mask + conditional subtract),
+    and — when oracle/_ref travelled — vs the reference's own sampler run with the fixed key of the harness."""
+    key = bytes(range(1, 33))
+    for bits, N, M in ((64, 1024, 4), (64, 64, 3), (32, 4096, 1), (32, 8, 2), (16, 512, 2), (16, 16, 1), (64, 4, 1), (32, 16384, 5)):
+        c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+        for batch, nonce in ((5, 0), (3, 2**32 - 1), (1, 2**63 + 7)):
+            d = c.alloc(batch)
+            c.uniform(d, batch, key, nonce)
+            got = np.empty((batch, M, N), c.dtype)
+            c.download(got, d, batch)
+            c.sync()
+            c.free(d)
+            assert np.array_equal(got, o.uniform(batch, key, nonce)), (bits, N, M, nonce)
+            assert all((got[:, cm, :] < c.moduli[cm]).all() for cm in range(M))
+    if have_ref():
+        for bits, N, M in ((64, 1024, 4), (32, 8, 2), (16, 512, 2)):
+            n0, ref = Ref(bits, N, M).uniform(4)
+            c = ctx_for(bits, N, M)
+            d = c.alloc(4)
+            c.uniform(d, 4, Ref.FIXED_KEY, n0)
+            got = np.empty((4, M, N), c.dtype)
+            c.download(got, d, 4)
+            c.sync()
+            c.free(d)
+            assert np.array_equal(got, ref)

@@ -115,3 +115,18 @@ def test_golden_params_match_live_reference():
         g = golden_params(bits)
         live = Ref.params(bits, 16)
         assert g == live
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so not built (needs /root/reference)")
+def test_oracle_uniform_sampler_matches_live_reference():
+    """poly::set(uniform) of the reference (its own Salsa20 assembly, keyed with the harness's fixed key) vs the oracle's
+    Salsa20 + mask/subtract restatement (core.hpp:150-187, fastrandombytes.cpp:21-34)."""
+    for bits, N, M in ((64, 1024, 4), (64, 64, 3), (32, 4096, 1), (32, 8, 2), (16, 512, 2), (16, 16, 1)):
+        n0, ref = Ref(bits, N, M).uniform(3)
+        assert np.array_equal(Oracle(bits, N, M).uniform(3, Ref.FIXED_KEY, n0), ref), (bits, N, M)
+
+
+def test_oracle_uniform_sampler_fixture():
+    k = np.load(os.path.join(GOLDEN, "uniform_u64_n1024_m4.npz"))
+    o = Oracle(64, 1024, 4)
+    assert np.array_equal(o.uniform(k["draws"].shape[0], bytes(k["key"]), int(k["first_nonce"])), k["draws"])
