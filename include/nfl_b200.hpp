@@ -569,6 +569,12 @@ public:
   void set_uniform(const uint8_t key[32], uint64_t first_nonce) {
     detail::check(nflgpu_uniform(ctx(), buf_.p, buf_.count, key, first_nonce, nullptr), "nflgpu_uniform");
   }
+  void set_non_uniform(uint64_t upper_bound, uint64_t amplifier, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:190-278
+    detail::check(nflgpu_non_uniform(ctx(), buf_.p, buf_.count, upper_bound, amplifier, key, first_nonce, nullptr), "nflgpu_non_uniform");
+  }
+  void set_zo(uint8_t rho, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:338-349
+    detail::check(nflgpu_zo(ctx(), buf_.p, buf_.count, rho, key, first_nonce, nullptr), "nflgpu_zo");
+  }
   // the cyclic transforms underneath (poly::core::ntt / inv_ntt, core.hpp:455-557; what tests/ntt_perfs.cpp times)
   void core_ntt() { detail::check(nflgpu_ntt_raw_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_fwd"); }
   void core_inv_ntt() { detail::check(nflgpu_ntt_raw_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_inv"); }

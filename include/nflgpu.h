@@ -150,6 +150,14 @@ int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, siz
  * by one conditional subtraction.  With the same 32-byte key the result is bit-identical to the reference's draws; the
  * caller owns key management (the reference keys itself once from /dev/urandom). */
 int nflgpu_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, const uint8_t key[32], uint64_t first_nonce, void *stream);
+/* poly::set(nfl::non_uniform(upper_bound, amplifier)) (core.hpp:190-278): centred noise in (-upper_bound, upper_bound)
+ * times `amplifier`, the same value in every residue (negative values stored as p_cm - |v|); one keystream of `degree`
+ * limbs per polynomial.  upper_bound >= a modulus is rejected like the reference's std::runtime_error (core.hpp:201-206). */
+int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_bound, uint64_t amplifier,
+                       const uint8_t key[32], uint64_t first_nonce, void *stream);
+/* poly::set(nfl::ZO_dist(rho)) (core.hpp:338-349, poly.hpp:59-62): coefficients in {-1, 0, 1} with P(+-1) = (rho/255)/2
+ * each, from one keystream byte per coefficient; -1 / +1 are stored as p_cm - 1 / p_cm + 1 exactly as the reference does. */
+int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream);
 
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked

@@ -56,6 +56,8 @@ def lib():
         L.nflgpu_muladd_shoup.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_host_op.argtypes = [vp, ci, vp, vp, vp, vp, sz]
         L.nflgpu_uniform.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.c_uint64, vp]
+        L.nflgpu_non_uniform.argtypes = [vp, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, vp]
+        L.nflgpu_zo.argtypes = [vp, vp, sz, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_eval.argtypes = [vp, vp, ctypes.POINTER(vp), sz, ctypes.c_char_p, sz, sz, vp]
         _lib = L
     return _lib
@@ -164,6 +166,12 @@ class Context:
     def uniform(self, dst, batch, key, first_nonce, stream=0):
         """nflgpu_uniform: `batch` poly::set(uniform) draws from the Salsa20 stream (key, first_nonce + i)."""
         _check(lib().nflgpu_uniform(self.h, dst, batch, bytes(key), first_nonce, stream))
+
+    def non_uniform(self, dst, batch, upper_bound, amplifier, key, first_nonce, stream=0):
+        _check(lib().nflgpu_non_uniform(self.h, dst, batch, upper_bound, amplifier, bytes(key), first_nonce, stream))
+
+    def zo(self, dst, batch, rho, key, first_nonce, stream=0):
+        _check(lib().nflgpu_zo(self.h, dst, batch, rho, bytes(key), first_nonce, stream))
 
     def eval(self, dst, operands, program, batch, stream=0):
         """nflgpu_eval: `operands` = list of device pointers, `program` = postfix bytes (see include/nflgpu.h)."""

@@ -6,6 +6,7 @@
 #include "pointwise.h"
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -425,7 +426,8 @@ int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t 
   return NFLGPU_OK;
 }
 
-int nflgpu_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+static int run_sampler(nflgpu_ctx *ctx, int kind, void *dst, size_t batch, const uint8_t *key, uint64_t first_nonce, uint64_t p0,
+                       uint64_t p1, uint64_t p2, size_t stream_bytes, void *stream) {
   int rc;
   if ((rc = check_buf(ctx, dst, "dst"))) return rc;
   if (!key) { set_error("null key"); return NFLGPU_ERR_ARG; }
@@ -439,12 +441,34 @@ int nflgpu_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, const uint8_t key[3
     a.key[i] = (uint32_t)key[4 * i] | ((uint32_t)key[4 * i + 1] << 8) | ((uint32_t)key[4 * i + 2] << 16) | ((uint32_t)key[4 * i + 3] << 24);
   a.first_nonce = first_nonce;
   a.poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
-  a.blocks_per_poly = (a.poly_bytes + 63) / 64;
+  a.blocks_per_poly = (stream_bytes + 63) / 64;  // keystream bytes one polynomial consumes
   a.nmoduli = (uint32_t)ctx->nmoduli; a.log2_degree = (uint32_t)ctx->log2_degree; a.limb_bits = (uint32_t)ctx->limb_bits;
   a.batch = (uint32_t)batch;
-  CUDA_TRY(launch_uniform(a, ctx->num_sms, (cudaStream_t)stream));
+  a.param0 = p0; a.param1 = p1; a.param2 = p2;
+  CUDA_TRY(launch_sampler(kind, a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return NFLGPU_OK;
+}
+
+int nflgpu_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  return run_sampler(ctx, SAMPLE_UNIFORM, dst, batch, key, first_nonce, 0, 0, 0, ctx->nmoduli * ctx->degree * ctx->limb_bytes, stream);
+}
+
+int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_bound, uint64_t amplifier, const uint8_t key[32],
+                       uint64_t first_nonce, void *stream) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  if (upper_bound == 0) { set_error("upper_bound must be positive"); return NFLGPU_ERR_ARG; }
+  for (uint64_t p : ctx->moduli)
+    if (upper_bound >= p) { set_error("core: upper_bound is larger than the modulus"); return NFLGPU_ERR_ARG; }  // core.hpp:201-206
+  // the reference computes the mask in double precision (core.hpp:218-219); reproduce that expression, not an integer log2
+  const uint64_t mask = (1ULL << (int)(std::floor(std::log2((double)(2 * upper_bound - 1))) + 1)) - 1;
+  return run_sampler(ctx, SAMPLE_NON_UNIFORM, dst, batch, key, first_nonce, upper_bound, amplifier, mask, ctx->degree * ctx->limb_bytes, stream);
+}
+
+int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  return run_sampler(ctx, SAMPLE_ZO, dst, batch, key, first_nonce, rho, 0, 0, ctx->degree, stream);
 }
 
 int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {

@@ -1,7 +1,9 @@
-// On-device uniform sampler: poly::set(nfl::uniform) for a whole batch, born in HBM.
+// On-device samplers: poly::set(nfl::uniform / non_uniform / ZO_dist) for a whole batch, born in HBM.
 //
 // Replaces, for device-resident batches, the reference's
 //   poly::set(uniform const&)              core.hpp:150-187   (mask every limb to the modulus' bit length, one conditional subtract)
+//   poly::set(non_uniform const&)          core.hpp:190-278   (centred bounded noise, same value in every residue)
+//   poly::set(ZO_dist const&)              core.hpp:338-349   ({-1,0,1} from one keystream byte per coefficient)
 //   nfl::fastrandombytes                    lib/prng/fastrandombytes.cpp:21-34  (Salsa20 keystream, one 64-bit nonce per call)
 //   nfl_crypto_stream_salsa20_amd64_xmm6    lib/prng/*.s       (Salsa20/20, D. J. Bernstein's public specification)
 // Polynomial i of the batch is filled from the keystream (key, first_nonce + i), exactly what `batch` successive
@@ -14,28 +16,90 @@ namespace nflgpu {
 
 __device__ __forceinline__ uint32_t rotl32(uint32_t v, int c) { return __funnelshift_l(v, v, c); }
 
+// one 64-byte Salsa20/20 keystream block (key, nonce, block counter) -> x[16] little-endian words
+__device__ __forceinline__ void salsa20_block(const uint32_t (&key)[8], uint64_t nonce, uint64_t blk, uint32_t (&x)[16]) {
+  uint32_t in[16];
+  in[0] = 0x61707865u; in[5] = 0x3320646eu; in[10] = 0x79622d32u; in[15] = 0x6b206574u;  // "expand 32-byte k"
+  in[1] = key[0]; in[2] = key[1]; in[3] = key[2]; in[4] = key[3];
+  in[11] = key[4]; in[12] = key[5]; in[13] = key[6]; in[14] = key[7];
+  in[6] = (uint32_t)nonce; in[7] = (uint32_t)(nonce >> 32); in[8] = (uint32_t)blk; in[9] = (uint32_t)(blk >> 32);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = in[i];
+#define NFLGPU_QR(A, B, C, D) \
+  x[B] ^= rotl32(x[A] + x[D], 7); x[C] ^= rotl32(x[B] + x[A], 9); x[D] ^= rotl32(x[C] + x[B], 13); x[A] ^= rotl32(x[D] + x[C], 18);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    NFLGPU_QR(0, 4, 8, 12) NFLGPU_QR(5, 9, 13, 1) NFLGPU_QR(10, 14, 2, 6) NFLGPU_QR(15, 3, 7, 11)
+    NFLGPU_QR(0, 1, 2, 3) NFLGPU_QR(5, 6, 7, 4) NFLGPU_QR(10, 11, 8, 9) NFLGPU_QR(15, 12, 13, 14)
+  }
+#undef NFLGPU_QR
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] += in[i];
+}
+
+template <class T> __device__ __forceinline__ void store_limb(void *base, uint64_t index, uint64_t v) { reinterpret_cast<T *>(base)[index] = (T)v; }
+__device__ __forceinline__ void store_any(void *base, uint32_t limb_bits, uint64_t index, uint64_t v) {
+  if (limb_bits == 64) store_limb<uint64_t>(base, index, v);
+  else if (limb_bits == 32) store_limb<uint32_t>(base, index, v);
+  else store_limb<uint16_t>(base, index, v);
+}
+
+// poly::set(non_uniform) core.hpp:190-278: one keystream of degree limbs per polynomial; coefficient i is the same
+// centred bounded value in every residue (p_cm - |v| for the negative half), optionally amplified.
+__global__ void __launch_bounds__(256) non_uniform_kernel(const SampleArgs a) {
+  const uint32_t limb_bytes = a.limb_bits / 8, per_block = 64 / limb_bytes;
+  const uint64_t degree = 1ull << a.log2_degree;
+  const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
+  const uint64_t wrap = a.limb_bits == 64 ? ~0ull : ((1ull << a.limb_bits) - 1);
+  const uint64_t two_ub_m1 = 2 * a.param0 - 1;
+  for (uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t poly = gb / a.blocks_per_poly, blk = gb - poly * a.blocks_per_poly;
+    uint32_t x[16];
+    salsa20_block(a.key, a.first_nonce + poly, blk, x);
+    for (uint32_t t = 0; t < per_block; ++t) {
+      const uint64_t i = blk * per_block + t;
+      if (i >= degree) break;
+      uint64_t raw;
+      if (a.limb_bits == 64) raw = ((uint64_t)x[2 * t + 1] << 32) | x[2 * t];
+      else if (a.limb_bits == 32) raw = x[t];
+      else raw = (x[t >> 1] >> (16 * (t & 1))) & 0xffffu;
+      uint64_t tmp = raw & a.param2;                                   // core.hpp:218-219,226
+      if (tmp >= two_ub_m1) tmp -= two_ub_m1;                           // core.hpp:232-234
+      for (uint32_t cm = 0; cm < a.nmoduli; ++cm) {
+        const uint64_t v = tmp >= a.param0 ? a.moduli[cm] + tmp * a.param1 - two_ub_m1 * a.param1 : tmp * a.param1;  // core.hpp:236-246,262-271
+        store_any(reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes, a.limb_bits, (uint64_t)cm * degree + i, v & wrap);
+      }
+    }
+  }
+}
+
+// poly::set(ZO_dist) core.hpp:338-349: one keystream BYTE per coefficient; {-1, 0, +1} stored as p-1 / 0 / p+1
+// (the reference really stores p + 1 for +1, core.hpp:347).
+__global__ void __launch_bounds__(256) zo_kernel(const SampleArgs a) {
+  const uint64_t degree = 1ull << a.log2_degree;
+  const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
+  for (uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t poly = gb / a.blocks_per_poly, blk = gb - poly * a.blocks_per_poly;
+    uint32_t x[16];
+    salsa20_block(a.key, a.first_nonce + poly, blk, x);
+    for (uint32_t t = 0; t < 64; ++t) {
+      const uint64_t i = blk * 64 + t;
+      if (i >= degree) break;
+      const uint32_t r = (x[t >> 2] >> (8 * (t & 3))) & 0xffu;
+      for (uint32_t cm = 0; cm < a.nmoduli; ++cm) {
+        const uint64_t v = r <= a.param0 ? (a.moduli[cm] - 1) + (r & 2) : 0;
+        store_any(reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes, a.limb_bits, (uint64_t)cm * degree + i, v);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) uniform_kernel(const SampleArgs a) {
   const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
   for (uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t poly = gb / a.blocks_per_poly, blk = gb - poly * a.blocks_per_poly;
-    const uint64_t nonce = a.first_nonce + poly;
-    uint32_t in[16], x[16];
-    in[0] = 0x61707865u; in[5] = 0x3320646eu; in[10] = 0x79622d32u; in[15] = 0x6b206574u;  // "expand 32-byte k"
-    in[1] = a.key[0]; in[2] = a.key[1]; in[3] = a.key[2]; in[4] = a.key[3];
-    in[11] = a.key[4]; in[12] = a.key[5]; in[13] = a.key[6]; in[14] = a.key[7];
-    in[6] = (uint32_t)nonce; in[7] = (uint32_t)(nonce >> 32); in[8] = (uint32_t)blk; in[9] = (uint32_t)(blk >> 32);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = in[i];
-#define NFLGPU_QR(A, B, C, D) \
-  x[B] ^= rotl32(x[A] + x[D], 7); x[C] ^= rotl32(x[B] + x[A], 9); x[D] ^= rotl32(x[C] + x[B], 13); x[A] ^= rotl32(x[D] + x[C], 18);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      NFLGPU_QR(0, 4, 8, 12) NFLGPU_QR(5, 9, 13, 1) NFLGPU_QR(10, 14, 2, 6) NFLGPU_QR(15, 3, 7, 11)
-      NFLGPU_QR(0, 1, 2, 3) NFLGPU_QR(5, 6, 7, 4) NFLGPU_QR(10, 11, 8, 9) NFLGPU_QR(15, 12, 13, 14)
-    }
-#undef NFLGPU_QR
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] += in[i];
+    uint32_t x[16];
+    salsa20_block(a.key, a.first_nonce + poly, blk, x);
 
     // mask + conditional subtract per limb (core.hpp:163-176); all limbs of a 64-byte block belong to one residue
     // whenever degree * limb_bytes >= 64, otherwise look the residue up per limb
@@ -93,12 +157,17 @@ __global__ void __launch_bounds__(256) uniform_kernel(const SampleArgs a) {
   }
 }
 
-cudaError_t launch_uniform(const SampleArgs &a, int num_sms, cudaStream_t stream) {
+cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream) {
   const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
   if (total == 0) return cudaSuccess;
   uint64_t blocks = (total + 255) / 256;
   if (blocks > (uint64_t)num_sms * 16) blocks = (uint64_t)num_sms * 16;
-  uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  switch (kind) {
+    case SAMPLE_UNIFORM: uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
+    case SAMPLE_NON_UNIFORM: non_uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
+    case SAMPLE_ZO: zo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 

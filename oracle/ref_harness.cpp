@@ -142,17 +142,24 @@ void randombytes(unsigned char *x, unsigned long long xlen) {
 }
 }
 static unsigned long long g_uniform_calls = 0;  // mirrors the nonce counter inside fastrandombytes.cpp:17-34
-template <class P> static void uniform_range(P *out, size_t batch) {
-  for (size_t i = 0; i < batch; ++i) { out[i].set(nfl::uniform()); ++g_uniform_calls; }
+template <class P> static void sample_range(int kind, P *out, size_t batch, unsigned long long p0, unsigned long long p1) {
+  for (size_t i = 0; i < batch; ++i) {
+    if (kind == 0) out[i].set(nfl::uniform());                       // core.hpp:150-187
+    else if (kind == 1) out[i].set(nfl::non_uniform(p0, p1));         // core.hpp:190-278
+    else out[i].set(nfl::ZO_dist((uint8_t)p0));                       // core.hpp:338-349
+    ++g_uniform_calls;  // every one of these draws makes exactly one fastrandombytes call
+  }
 }
 #define NFLREF_UNIFORM(T, BITS, N, M) \
-  if (limb_bits == BITS && degree == N && nmoduli == M) { uniform_range(static_cast<nfl::poly<T, N, M> *>(out), batch); return 0; }
+  if (limb_bits == BITS && degree == N && nmoduli == M) { sample_range(kind, static_cast<nfl::poly<T, N, M> *>(out), batch, p0, p1); return 0; }
 extern "C" {
 
 // out[0..batch) = successive poly::set(nfl::uniform()) draws; *first_nonce receives the 64-bit nonce the first of
 // them used (one fastrandombytes call, i.e. one nonce, per polynomial).  Single-threaded: the reference's PRNG state
 // is a process-global static.
-int nflref_uniform(int limb_bits, size_t degree, size_t nmoduli, void *out, size_t batch, unsigned long long *first_nonce) {
+// kind: 0 uniform, 1 non_uniform(p0 = upper_bound, p1 = amplifier), 2 ZO_dist(p0 = rho)
+int nflref_sample(int kind, int limb_bits, size_t degree, size_t nmoduli, void *out, size_t batch, unsigned long long p0,
+                  unsigned long long p1, unsigned long long *first_nonce) {
   if (reinterpret_cast<uintptr_t>(out) & 31) return -2;
   *first_nonce = g_uniform_calls;
   NFLREF_UNIFORM(uint64_t, 64, 1024, 4) NFLREF_UNIFORM(uint64_t, 64, 64, 3) NFLREF_UNIFORM(uint32_t, 32, 4096, 1)

@@ -56,6 +56,8 @@ class Oracle:
             L.nflo_run.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 4 + [ctypes.c_size_t]
             L.nflo_spec_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
             L.nflo_uniform.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64]
+            L.nflo_non_uniform.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64]
+            L.nflo_zo.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64]
             cls._lib = L
         return cls._lib
 
@@ -90,6 +92,16 @@ class Oracle:
         """`batch` successive poly::set(uniform) draws from the Salsa20 stream (key, first_nonce + i)."""
         out = np.empty((batch, self.M, self.N), dtype=self.dtype)
         self.lib().nflo_uniform(self.h, out.ctypes.data, batch, bytes(key), first_nonce)
+        return out
+
+    def non_uniform(self, batch, upper_bound, amplifier, key, first_nonce):
+        out = np.empty((batch, self.M, self.N), dtype=self.dtype)
+        self.lib().nflo_non_uniform(self.h, out.ctypes.data, batch, upper_bound, amplifier, bytes(key), first_nonce)
+        return out
+
+    def zo(self, batch, rho, key, first_nonce):
+        out = np.empty((batch, self.M, self.N), dtype=self.dtype)
+        self.lib().nflo_zo(self.h, out.ctypes.data, batch, rho, bytes(key), first_nonce)
         return out
 
     def spec_fwd(self, a):
@@ -137,15 +149,20 @@ class Ref:
 
     FIXED_KEY = bytes(range(1, 33))  # what the harness's randombytes stub hands to fastrandombytes.cpp
 
-    def uniform(self, batch):
-        """(first_nonce, polys): the reference's own poly::set(uniform) run `batch` times with the fixed key."""
+    def sample(self, kind, batch, p0=0, p1=0):
+        """(first_nonce, polys): the reference's own poly::set(uniform | non_uniform(p0, p1) | ZO_dist(p0)) run `batch` times
+        with the fixed Salsa20 key of the harness."""
         out = aligned((batch, self.M, self.N), self.dtype)
         n = ctypes.c_ulonglong()
-        self.lib().nflref_uniform.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
-                                              ctypes.POINTER(ctypes.c_ulonglong)]
-        rc = self.lib().nflref_uniform(self.bits, self.N, self.M, out.ctypes.data, batch, ctypes.byref(n))
+        self.lib().nflref_sample.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]
+        rc = self.lib().nflref_sample({"uniform": 0, "non_uniform": 1, "zo": 2}[kind], self.bits, self.N, self.M, out.ctypes.data, batch, p0, p1,
+                                      ctypes.byref(n))
         assert rc == 0, rc
         return n.value, out
+
+    def uniform(self, batch):
+        return self.sample("uniform", batch)
 
     @classmethod
     def params(cls, bits, count):

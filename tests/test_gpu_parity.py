@@ -295,3 +295,39 @@ def test_uniform_sampler_matches_reference_draws():
             c.sync()
             c.free(d)
             assert np.array_equal(got, ref)
+
+
+def test_bounded_and_zo_samplers():
+    """nflgpu_non_uniform / nflgpu_zo vs the oracle restatements of core.hpp:190-278 / 338-349 (pinned against the reference's
+    own samplers in tests/test_oracle.py) and, when it travelled, the live reference."""
+    key = bytes(range(1, 33))
+    for bits, N, M in ((64, 1024, 4), (32, 8, 2), (16, 512, 2), (32, 4096, 3), (64, 16, 2)):
+        c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+        batch = 4
+        d = c.alloc(batch)
+        got = np.empty((batch, M, N), c.dtype)
+        for ub, amp in ((1, 1), (5, 3), (1 << 10, 1), (1000, 7)):
+            c.non_uniform(d, batch, ub, amp, key, 77)
+            c.download(got, d, batch); c.sync()
+            assert np.array_equal(got, o.non_uniform(batch, ub, amp, key, 77)), (bits, N, M, ub, amp)
+        for rho in (0, 0x7F, 0xFF):
+            c.zo(d, batch, rho, key, 1234)
+            c.download(got, d, batch); c.sync()
+            assert np.array_equal(got, o.zo(batch, rho, key, 1234)), (bits, N, M, rho)
+        with pytest.raises(nb.NflGpuError):
+            c.non_uniform(d, batch, int(c.moduli.min()), 1, key, 0)   # core.hpp:201-206
+        c.free(d)
+    if have_ref():
+        bits, N, M = 64, 1024, 4
+        r, c = Ref(bits, N, M), ctx_for(bits, N, M)
+        d = c.alloc(3)
+        got = np.empty((3, M, N), c.dtype)
+        n0, ref = r.sample("non_uniform", 3, 9, 2)
+        c.non_uniform(d, 3, 9, 2, Ref.FIXED_KEY, n0)
+        c.download(got, d, 3); c.sync()
+        assert np.array_equal(got, ref)
+        n0, ref = r.sample("zo", 3, 0x7F)
+        c.zo(d, 3, 0x7F, Ref.FIXED_KEY, n0)
+        c.download(got, d, 3); c.sync()
+        assert np.array_equal(got, ref)
+        c.free(d)

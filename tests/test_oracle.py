@@ -126,6 +126,18 @@ def test_oracle_uniform_sampler_matches_live_reference():
         assert np.array_equal(Oracle(bits, N, M).uniform(3, Ref.FIXED_KEY, n0), ref), (bits, N, M)
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so not built (needs /root/reference)")
+def test_oracle_bounded_and_zo_samplers_match_live_reference():
+    for bits, N, M in ((64, 1024, 4), (32, 8, 2), (16, 512, 2)):
+        r, o = Ref(bits, N, M), Oracle(bits, N, M)
+        for ub, amp in ((1, 1), (2, 1), (5, 3), (1 << 10, 1), (1000, 7)):
+            n0, ref = r.sample("non_uniform", 3, ub, amp)
+            assert np.array_equal(o.non_uniform(3, ub, amp, Ref.FIXED_KEY, n0), ref), (bits, N, M, ub, amp)
+        for rho in (0, 1, 0x7F, 0xFF):
+            n0, ref = r.sample("zo", 3, rho)
+            assert np.array_equal(o.zo(3, rho, Ref.FIXED_KEY, n0), ref), (bits, N, M, rho)
+
+
 def test_oracle_uniform_sampler_fixture():
     k = np.load(os.path.join(GOLDEN, "uniform_u64_n1024_m4.npz"))
     o = Oracle(64, 1024, 4)
