@@ -67,16 +67,17 @@ template <> struct Arith<16> {
 
 // x - (x >= m ? m : 0)
 template <class W> static __device__ __forceinline__ W csub(W x, W m) { return x >= m ? x - m : x; }
+// 32-bit words, x < 2m, m <= 2^31 (every use in this library): one VIADDMNMX.U32 — see csub_lazy below
+template <> __device__ __forceinline__ uint32_t csub<uint32_t>(uint32_t x, uint32_t m) { return min(x, x - m); }
 // Same, for the lazy-range reductions where m <= 2^(w-1) and x < 2m: the sign of x - m decides, which costs one
 // compare on the high word instead of a two-instruction 64-bit unsigned compare.
 static __device__ __forceinline__ uint64_t csub_lazy(uint64_t x, uint64_t m) {
   const int64_t t = (int64_t)(x - m);
   return t < 0 ? x : (uint64_t)t;
 }
-static __device__ __forceinline__ uint32_t csub_lazy(uint32_t x, uint32_t m) {
-  const int32_t t = (int32_t)(x - m);
-  return t < 0 ? x : (uint32_t)t;
-}
+// 32-bit words: the wrapped difference is larger than x exactly when x < m, so an unsigned minimum does the select
+// (IADD3 + VIMNMX.U32: two ALU instructions instead of three)
+static __device__ __forceinline__ uint32_t csub_lazy(uint32_t x, uint32_t m) { return min(x, x - m); }
 // -p mod 2^w, hidden from constant propagation so products with it are not rewritten back into subtractions
 static __device__ __forceinline__ uint64_t opaque_neg(uint64_t p) { uint64_t n = (uint64_t)0 - p; asm("" : "+l"(n)); return n; }
 static __device__ __forceinline__ uint32_t opaque_neg(uint32_t p) { uint32_t n = (uint32_t)0 - p; asm("" : "+r"(n)); return n; }

@@ -7,7 +7,7 @@ import subprocess
 import sys
 from collections import Counter
 
-ALU = ("IADD3", "LOP3", "SEL", "ISETP", "SHF", "LEA", "MOV", "PRMT", "VIADD", "IMNMX", "VIMNMX", "PLOP3", "FSEL", "IABS", "BMSK", "SGXT", "FLO", "POPC", "CS2R")
+ALU = ("IADD3", "LOP3", "SEL", "ISETP", "SHF", "LEA", "MOV", "PRMT", "VIADD", "VIADDMNMX", "IMNMX", "VIMNMX", "PLOP3", "FSEL", "IABS", "BMSK", "SGXT", "FLO", "POPC", "CS2R")
 
 
 def kernels(path, hot_loop=True):
