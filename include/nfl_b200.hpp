@@ -575,6 +575,11 @@ public:
   void set_zo(uint8_t rho, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:338-349
     detail::check(nflgpu_zo(ctx(), buf_.p, buf_.count, rho, key, first_nonce, nullptr), "nflgpu_zo");
   }
+  // CRT lift (poly::GMP::poly2mpz / mpz2poly, gmp.hpp:183-219) without GMP types: `words` is a device buffer of
+  // size() * degree * lift_words() uint64_t, each coefficient as little-endian 64-bit words (mpz_export layout)
+  static size_t lift_words() { size_t w = 0; detail::check(nflgpu_lift_words(ctx(), &w), "nflgpu_lift_words"); return w; }
+  void poly2words(uint64_t *device_words) const { detail::check(nflgpu_poly2mpz(ctx(), device_words, buf_.p, buf_.count, nullptr), "nflgpu_poly2mpz"); }
+  void words2poly(const uint64_t *device_words) { detail::check(nflgpu_mpz2poly(ctx(), buf_.p, device_words, buf_.count, nullptr), "nflgpu_mpz2poly"); }
   // the cyclic transforms underneath (poly::core::ntt / inv_ntt, core.hpp:455-557; what tests/ntt_perfs.cpp times)
   void core_ntt() { detail::check(nflgpu_ntt_raw_fwd(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_fwd"); }
   void core_inv_ntt() { detail::check(nflgpu_ntt_raw_inv(ctx(), buf_.p, buf_.p, buf_.count, nullptr), "nflgpu_ntt_raw_inv"); }

@@ -159,6 +159,18 @@ int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_
  * each, from one keystream byte per coefficient; -1 / +1 are stored as p_cm - 1 / p_cm + 1 exactly as the reference does. */
 int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream);
 
+/* ---- CRT lift: the consumer that needs all residues of a polynomial on one device ------------------------- */
+
+/* poly::GMP::poly2mpz / mpz2poly (include/nfl/gmp.hpp:183-219) without GMP types: a lifted coefficient is
+ * W = ceil(bits(prod p_cm) / 64) little-endian 64-bit words (what mpz_export(w, 0, -1, 8, 0, 0, x) writes);
+ * word buffers are uint64_t[batch][degree][W] in device memory.  nflgpu_lift_words reports W (at most 16, i.e. moduli
+ * products up to 1024 bits; larger ones return NFLGPU_ERR_UNSUPPORTED).
+ *   poly2mpz: x_i = the unique integer in [0, prod p_cm) with x_i = src[cm][i] (mod p_cm) for every residue
+ *   mpz2poly: dst[cm][i] = x_i mod p_cm */
+int nflgpu_lift_words(nflgpu_ctx *ctx, size_t *words_per_coefficient);
+int nflgpu_poly2mpz(nflgpu_ctx *ctx, uint64_t *dst_words, const void *src_polys, size_t batch, void *stream);
+int nflgpu_mpz2poly(nflgpu_ctx *ctx, void *dst_polys, const uint64_t *src_words, size_t batch, void *stream);
+
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked
  * and double-buffered over two streams.  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,

@@ -58,6 +58,9 @@ def lib():
         L.nflgpu_uniform.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_non_uniform.argtypes = [vp, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_zo.argtypes = [vp, vp, sz, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64, vp]
+        L.nflgpu_lift_words.argtypes = [vp, ctypes.POINTER(sz)]
+        L.nflgpu_poly2mpz.argtypes = [vp, vp, vp, sz, vp]
+        L.nflgpu_mpz2poly.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_eval.argtypes = [vp, vp, ctypes.POINTER(vp), sz, ctypes.c_char_p, sz, sz, vp]
         _lib = L
     return _lib
@@ -172,6 +175,17 @@ class Context:
 
     def zo(self, dst, batch, rho, key, first_nonce, stream=0):
         _check(lib().nflgpu_zo(self.h, dst, batch, rho, bytes(key), first_nonce, stream))
+
+    def lift_words(self):
+        w = ctypes.c_size_t()
+        _check(lib().nflgpu_lift_words(self.h, ctypes.byref(w)))
+        return w.value
+
+    def poly2mpz(self, dst_words, src_polys, batch, stream=0):
+        _check(lib().nflgpu_poly2mpz(self.h, dst_words, src_polys, batch, stream))
+
+    def mpz2poly(self, dst_polys, src_words, batch, stream=0):
+        _check(lib().nflgpu_mpz2poly(self.h, dst_polys, src_words, batch, stream))
 
     def eval(self, dst, operands, program, batch, stream=0):
         """nflgpu_eval: `operands` = list of device pointers, `program` = postfix bytes (see include/nflgpu.h)."""

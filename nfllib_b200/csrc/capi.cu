@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every compute entry point ends in a kernel launch or fails.
 #include "../../include/nflgpu.h"
 #include "host_common.hpp"
+#include "lift.h"
 #include "ntt_dispatch.h"
 #include "pointwise.h"
 
@@ -70,6 +71,9 @@ struct nflgpu_ctx {
   void *d_tw_raw_fwd = nullptr, *d_tw_raw_inv = nullptr;  // cyclic (no-twist) tables, built on first use
   std::vector<uint64_t> roots;
   uint64_t kmax = 0;
+  // CRT-lift tables, built on first use (lift.cu)
+  int lift_words = 0;
+  uint64_t *d_lift = nullptr;  // [inv | c64 | qhat (M*W) | q (W)]
   std::atomic<uint64_t> launches{0};
   static constexpr int kStages = 4;
   HostStage stage[kStages];
@@ -301,7 +305,7 @@ int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
     for (int i = 0; i < 4; ++i) { if (s.dev[i]) cudaFree(s.dev[i]); if (s.pin[i]) cudaFreeHost(s.pin[i]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
+  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
   delete ctx;
   return NFLGPU_OK;
 }
@@ -434,6 +438,87 @@ int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t 
   CUDA_TRY(launch_eval(ctx->limb_bits, a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return NFLGPU_OK;
+}
+
+// ---- CRT lift (gmp.hpp:113-219) ----------------------------------------------------------------------------------
+namespace {
+typedef std::vector<uint64_t> Big;  // little-endian 64-bit words
+Big big_mul_small(const Big &a, uint64_t m) {
+  Big r(a.size() + 1, 0);
+  unsigned __int128 carry = 0;
+  for (size_t i = 0; i < a.size(); ++i) { carry += (unsigned __int128)a[i] * m; r[i] = (uint64_t)carry; carry >>= 64; }
+  r[a.size()] = (uint64_t)carry;
+  while (r.size() > 1 && r.back() == 0) r.pop_back();
+  return r;
+}
+uint64_t big_mod_small(const Big &a, uint64_t m) {
+  unsigned __int128 r = 0;
+  for (size_t i = a.size(); i-- > 0;) r = ((r << 64) | a[i]) % m;
+  return (uint64_t)r;
+}
+size_t big_bits(const Big &a) {
+  size_t top = a.size() - 1;
+  return a[top] ? top * 64 + (64 - __builtin_clzll(a[top])) : 0;
+}
+// moduli product, Q/p_cm, their inverses (gmp.hpp:116-150) -> device
+int ensure_lift_tables(nflgpu_ctx *ctx) {
+  if (ctx->d_lift) return NFLGPU_OK;
+  const size_t M = ctx->nmoduli;
+  Big Q(1, 1);
+  for (uint64_t p : ctx->moduli) Q = big_mul_small(Q, p);
+  const size_t W = (big_bits(Q) + 63) / 64;
+  if (W > LIFT_MAX_WORDS) { set_error("CRT lift supports moduli products of at most 1024 bits"); return NFLGPU_ERR_UNSUPPORTED; }
+  std::vector<uint64_t> host(2 * M + M * W + W, 0);
+  for (size_t cm = 0; cm < M; ++cm) {
+    Big qh(1, 1);
+    for (size_t j = 0; j < M; ++j) if (j != cm) qh = big_mul_small(qh, ctx->moduli[j]);
+    const uint64_t p = ctx->moduli[cm];
+    host[cm] = invmod64(big_mod_small(qh, p), p);
+    host[M + cm] = (uint64_t)((((unsigned __int128)1) << 64) % p);
+    for (size_t k = 0; k < qh.size() && k < W; ++k) host[2 * M + cm * W + k] = qh[k];
+  }
+  for (size_t k = 0; k < Q.size() && k < W; ++k) host[2 * M + M * W + k] = Q[k];
+  cudaError_t e;
+  if ((e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_lift), host.size() * 8)) != cudaSuccess ||
+      (e = cudaMemcpy(ctx->d_lift, host.data(), host.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    set_error(std::string("lift table upload: ") + cudaGetErrorName(e));
+    return NFLGPU_ERR_CUDA;
+  }
+  ctx->lift_words = (int)W;
+  return NFLGPU_OK;
+}
+int run_lift(nflgpu_ctx *ctx, int dir, void *polys, uint64_t *words, size_t batch, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, polys, "polys"))) return rc;
+  if (!words || (reinterpret_cast<uintptr_t>(words) & 7)) { set_error("bad words buffer"); return NFLGPU_ERR_ARG; }
+  if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  if ((rc = ensure_lift_tables(ctx))) return rc;
+  const size_t M = ctx->nmoduli, W = ctx->lift_words;
+  LiftArgs a;
+  a.polys = polys; a.words = words; a.moduli = ctx->d_moduli64; a.consts = ctx->d_consts;
+  a.inv = ctx->d_lift; a.c64 = ctx->d_lift + M; a.qhat = ctx->d_lift + 2 * M; a.q = ctx->d_lift + 2 * M + M * W;
+  a.nmoduli = (uint32_t)M; a.log2_degree = (uint32_t)ctx->log2_degree; a.batch = (uint32_t)batch;
+  CUDA_TRY(launch_lift(ctx->limb_bits, dir, (int)W, a, ctx->num_sms, (cudaStream_t)stream));
+  ctx->launches++;
+  return NFLGPU_OK;
+}
+}  // namespace
+
+int nflgpu_lift_words(nflgpu_ctx *ctx, size_t *words_per_coefficient) {
+  if (!ctx || !words_per_coefficient) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  if (int rc = ensure_lift_tables(ctx)) return rc;
+  *words_per_coefficient = ctx->lift_words;
+  return NFLGPU_OK;
+}
+int nflgpu_poly2mpz(nflgpu_ctx *ctx, uint64_t *dst_words, const void *src_polys, size_t batch, void *stream) {
+  return run_lift(ctx, 0, const_cast<void *>(src_polys), dst_words, batch, stream);
+}
+int nflgpu_mpz2poly(nflgpu_ctx *ctx, void *dst_polys, const uint64_t *src_words, size_t batch, void *stream) {
+  return run_lift(ctx, 1, dst_polys, const_cast<uint64_t *>(src_words), batch, stream);
 }
 
 static int run_sampler(nflgpu_ctx *ctx, int kind, void *dst, size_t batch, const uint8_t *key, uint64_t first_nonce, uint64_t p0,

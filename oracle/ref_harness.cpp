@@ -14,6 +14,7 @@
 //   compute_shoup -> nfl::compute_shoup(a)            include/nfl/poly.hpp:352
 //   raw_ntt / raw_intt -> poly::core::ntt / inv_ntt via the friend proxy, as tests/ntt_perfs.cpp:122-134 does
 //   polymul    -> fwd(a), fwd(b), a*b, inv            (tests/nfllib_demo_main_op.cpp:31-45 pattern)
+#include <array>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -128,6 +129,45 @@ int NFLREF_CAT(nflref_run_part, NFLREF_PART)(int op, int limb_bits, size_t degre
 #include "ref_configs.inc"
   return -1;
 }
+
+#if NFLREF_PART == 2
+}  // extern "C"
+// CRT lift through the reference's own GMP code (gmp.hpp:183-219), linked against the image's libgmp runtime.
+// words: [batch][degree][W] little-endian 64-bit words of each lifted coefficient (mpz_export, least significant first).
+template <class P> static int lift_config(int dir, void *polys, uint64_t *words, size_t W, size_t batch) {
+  P *p = static_cast<P *>(polys);
+  std::array<mpz_t, P::degree> *arr = new std::array<mpz_t, P::degree>;
+  for (size_t i = 0; i < P::degree; ++i) mpz_init((*arr)[i]);
+  for (size_t b = 0; b < batch; ++b) {
+    if (dir == 0) {  // poly2mpz
+      p[b].poly2mpz(*arr);
+      for (size_t i = 0; i < P::degree; ++i) {
+        uint64_t *w = words + (b * P::degree + i) * W;
+        std::memset(w, 0, W * 8);
+        size_t count = 0;
+        if (mpz_sizeinbase((*arr)[i], 2) > 64 * W) return -3;
+        mpz_export(w, &count, -1, 8, 0, 0, (*arr)[i]);
+      }
+    } else {  // mpz2poly
+      for (size_t i = 0; i < P::degree; ++i) mpz_import((*arr)[i], W, -1, 8, 0, 0, words + (b * P::degree + i) * W);
+      p[b].mpz2poly(*arr);
+    }
+  }
+  for (size_t i = 0; i < P::degree; ++i) mpz_clear((*arr)[i]);
+  delete arr;
+  return 0;
+}
+#define NFLREF_LIFT(T, BITS, N, M) \
+  if (limb_bits == BITS && degree == N && nmoduli == M) return lift_config<nfl::poly<T, N, M>>(dir, polys, words, W, batch);
+extern "C" {
+// dir 0: words = poly2mpz(polys);  dir 1: polys = mpz2poly(words).  Returns -1 for a configuration that is not built.
+int nflref_lift(int dir, int limb_bits, size_t degree, size_t nmoduli, void *polys, uint64_t *words, size_t W, size_t batch) {
+  if (reinterpret_cast<uintptr_t>(polys) & 31) return -2;
+  NFLREF_LIFT(uint64_t, 64, 1024, 4) NFLREF_LIFT(uint64_t, 64, 64, 3) NFLREF_LIFT(uint64_t, 64, 1024, 2)
+  NFLREF_LIFT(uint32_t, 32, 1024, 2) NFLREF_LIFT(uint32_t, 32, 4096, 14) NFLREF_LIFT(uint16_t, 16, 512, 2)
+  return -1;
+}
+#endif
 
 #if NFLREF_PART == 0
 

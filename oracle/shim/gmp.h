@@ -19,6 +19,35 @@ typedef __mpz_struct mpz_t[1];
 typedef __mpz_struct *mpz_ptr;
 typedef const __mpz_struct *mpz_srcptr;
 
+/* The runtime library (libgmp.so.10, present in the image) exports these functions under the __gmpz_ prefix; the real
+ * <gmp.h> maps the public names with macros exactly like this.  With them the reference's CRT-lifting code
+ * (include/nfl/gmp.hpp) links against the installed runtime although its development headers are absent. */
+#define mpz_init2 __gmpz_init2
+#define mpz_inits __gmpz_inits
+#define mpz_clear __gmpz_clear
+#define mpz_clears __gmpz_clears
+#define mpz_init_set_ui __gmpz_init_set_ui
+#define mpz_set_ui __gmpz_set_ui
+#define mpz_mul __gmpz_mul
+#define mpz_mul_ui __gmpz_mul_ui
+#define mpz_addmul_ui __gmpz_addmul_ui
+#define mpz_sub __gmpz_sub
+#define mpz_submul __gmpz_submul
+#define mpz_divexact __gmpz_divexact
+#define mpz_tdiv_q __gmpz_tdiv_q
+#define mpz_tdiv_q_2exp __gmpz_tdiv_q_2exp
+#define mpz_ui_pow_ui __gmpz_ui_pow_ui
+#define mpz_invert __gmpz_invert
+#define mpz_cmp __gmpz_cmp
+#define mpz_fdiv_ui __gmpz_fdiv_ui
+#define mpz_sizeinbase __gmpz_sizeinbase
+#define mpz_out_str __gmpz_out_str
+#define mpz_export __gmpz_export
+#define mpz_import __gmpz_import
+#define mpz_init __gmpz_init
+
+void mpz_init(mpz_ptr);
+void mpz_import(mpz_ptr, size_t, int, size_t, int, size_t, const void *);
 void mpz_init2(mpz_ptr, mp_bitcnt_t);
 void mpz_inits(mpz_ptr, ...);
 void mpz_clear(mpz_ptr);

@@ -51,6 +51,10 @@ def main():
     np.savez_compressed(os.path.join(GOLDEN, "uniform_u64_n1024_m4.npz"), draws=draws, key=np.frombuffer(Ref.FIXED_KEY, dtype=np.uint8),
                         first_nonce=np.uint64(n0))
 
+    # CRT lift by the reference's GMP code (gmp.hpp:183-219)
+    lp = random_polys(64, 64, 3, 3, 808, params[64]["P"])
+    np.savez_compressed(os.path.join(GOLDEN, "lift_u64_n64_m3.npz"), polys=lp, words=Ref(64, 64, 3).lift(lp, 3))
+
     # hashes at the BASELINE.json configurations (batch kept small; inputs are seeded, see random_polys)
     hashes = {}
     for name, bits, N, M, batch in [("C1", 64, 1024, 1, 4), ("C2", 64, 1024, 4, 16), ("C3", 64, 16384, 8, 2), ("C4", 32, 4096, 14, 4),

@@ -164,6 +164,25 @@ class Ref:
     def uniform(self, batch):
         return self.sample("uniform", batch)
 
+    def lift(self, polys, W):
+        """The reference's own poly2mpz (GMP runtime of the image): uint64[batch][N][W]."""
+        polys = as_aligned(np.ascontiguousarray(polys, dtype=self.dtype))
+        words = np.zeros((polys.shape[0], self.N, W), np.uint64)
+        L = self.lib()
+        L.nflref_lift.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+        rc = L.nflref_lift(0, self.bits, self.N, self.M, polys.ctypes.data, words.ctypes.data, W, polys.shape[0])
+        assert rc == 0, rc
+        return words
+
+    def unlift(self, words):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        out = aligned((words.shape[0], self.M, self.N), self.dtype)
+        L = self.lib()
+        L.nflref_lift.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+        rc = L.nflref_lift(1, self.bits, self.N, self.M, out.ctypes.data, words.ctypes.data, words.shape[2], words.shape[0])
+        assert rc == 0, rc
+        return out
+
     @classmethod
     def params(cls, bits, count):
         L = cls.lib()
@@ -173,6 +192,48 @@ class Ref:
         n = min(count, mm.value)
         return {"P": [int(v) for v in arrs[0][:n]], "Pn": [int(v) for v in arrs[1][:n]], "roots": [int(v) for v in arrs[2][:n]],
                 "invkmax": [int(v) for v in arrs[3][:n]], "kmax": k.value, "maxmoduli": mm.value}
+
+
+def lift_words_per_coeff(P):
+    q = 1
+    for p in P:
+        q *= int(p)
+    return (q.bit_length() + 63) // 64
+
+
+def crt_lift(polys, P):
+    """Big-integer restatement of poly::GMP::poly2mpz (gmp.hpp:183-209): for every coefficient the unique x in [0, prod P) with
+    x = a_cm (mod p_cm); returned as uint64[batch][N][W] little-endian words (the layout mpz_export(..., -1, 8, 0, 0, x) gives)."""
+    P = [int(p) for p in P]
+    Q = 1
+    for p in P:
+        Q *= p
+    L = [(Q // p) * pow(Q // p, -1, p) for p in P]  # lifting_integers, gmp.hpp:137-150
+    W = (Q.bit_length() + 63) // 64
+    batch, M, N = polys.shape
+    out = np.zeros((batch, N, W), np.uint64)
+    for b in range(batch):
+        cols = [polys[b, cm].astype(object) * L[cm] for cm in range(M)]
+        x = cols[0]
+        for c in cols[1:]:
+            x = x + c
+        x = x % Q
+        for k in range(W):
+            out[b, :, k] = ((x >> (64 * k)) & 0xFFFFFFFFFFFFFFFF).astype(np.uint64)
+    return out
+
+
+def crt_unlift(words, P, dtype):
+    """poly::GMP::mpz2poly (gmp.hpp:211-219): a[cm][i] = x_i mod p_cm."""
+    batch, N, W = words.shape
+    out = np.zeros((batch, len(P), N), dtype)
+    for b in range(batch):
+        x = np.zeros(N, dtype=object)
+        for k in range(W):
+            x = x + (words[b, :, k].astype(object) << (64 * k))
+        for cm, p in enumerate(P):
+            out[b, cm] = (x % int(p)).astype(dtype)
+    return out
 
 
 def splitmix64(seed, n):

@@ -15,7 +15,7 @@ import re
 import numpy as np
 import pytest
 
-from oracle_lib import GOLDEN, Oracle, Ref, have_ref, golden_params, random_polys
+from oracle_lib import GOLDEN, DTYPES, Oracle, Ref, have_ref, golden_params, random_polys, crt_lift, crt_unlift, lift_words_per_coeff
 
 pytestmark = pytest.mark.gpu
 
@@ -331,3 +331,40 @@ def test_bounded_and_zo_samplers():
         c.download(got, d, 3); c.sync()
         assert np.array_equal(got, ref)
         c.free(d)
+
+
+def test_crt_lift_matches_oracle_and_reference():
+    """nflgpu_poly2mpz / nflgpu_mpz2poly (gmp.hpp:183-219) vs the big-integer restatement (pinned against the reference's GMP
+    code in tests/test_oracle.py) and the live reference when it travelled."""
+    import torch
+    for bits, N, M in ((64, 1024, 4), (64, 64, 3), (32, 1024, 2), (32, 4096, 14), (16, 512, 2), (64, 1024, 1), (64, 256, 16)):
+        c = ctx_for(bits, N, M)
+        P = [int(p) for p in c.moduli]
+        a = random_polys(bits, N, M, 3, 55, P=P)
+        e = np.zeros((3, M, N), c.dtype)
+        for cm in range(M):
+            e[1, cm, :] = P[cm] - 1
+        e[2, 0, :] = 1
+        a = np.concatenate([a, e])
+        batch = a.shape[0]
+        W = c.lift_words()
+        assert W == lift_words_per_coeff(P)
+        dp = c.alloc(batch)
+        c.upload(dp, a, batch)
+        dw = torch.zeros((batch, N, W), dtype=torch.int64, device="cuda")
+        c.poly2mpz(dw.data_ptr(), dp, batch)
+        c.sync()
+        words = dw.cpu().numpy().view(np.uint64)
+        exp = crt_lift(a, P)
+        assert np.array_equal(words, exp), (bits, N, M)
+        back = c.alloc(batch)
+        c.mpz2poly(back, dw.data_ptr(), batch)
+        got = np.empty_like(a)
+        c.download(got, back, batch)
+        c.sync()
+        assert np.array_equal(got, a)
+        if have_ref() and Ref(bits, N, M).supported() and (bits, N, M) in ((64, 1024, 4), (32, 4096, 14), (16, 512, 2)):
+            assert np.array_equal(words, Ref(bits, N, M).lift(a, W))
+        c.free(dp); c.free(back)
+    with pytest.raises(nb.NflGpuError):
+        ctx_for(64, 64, 17).lift_words()   # 17 * 62 bits > 1024

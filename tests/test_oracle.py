@@ -13,7 +13,7 @@ import re
 import numpy as np
 import pytest
 
-from oracle_lib import GOLDEN, DTYPES, Oracle, Ref, have_ref, golden_params, random_polys
+from oracle_lib import GOLDEN, DTYPES, Oracle, Ref, have_ref, golden_params, random_polys, crt_lift, crt_unlift, lift_words_per_coeff
 
 KATS = sorted(glob.glob(os.path.join(GOLDEN, "kat_*.npz")))
 
@@ -142,3 +142,34 @@ def test_oracle_uniform_sampler_fixture():
     k = np.load(os.path.join(GOLDEN, "uniform_u64_n1024_m4.npz"))
     o = Oracle(64, 1024, 4)
     assert np.array_equal(o.uniform(k["draws"].shape[0], bytes(k["key"]), int(k["first_nonce"])), k["draws"])
+
+
+def _lift_cases(bits, N, M):
+    P = golden_params(bits)["P"][:M]
+    a = random_polys(bits, N, M, 2, 55)
+    e = np.zeros((3, M, N), DTYPES[bits])
+    for cm in range(M):
+        e[1, cm, :] = P[cm] - 1          # lifts to Q - 1
+    e[2, 0, :] = 1                       # only one residue non-zero
+    return P, np.concatenate([a, e])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so not built (needs /root/reference)")
+def test_crt_lift_restatement_matches_live_reference():
+    """poly2mpz / mpz2poly of the reference (its GMP code, gmp.hpp:183-219, linked against the image's libgmp runtime) vs the
+    big-integer restatement in oracle_lib."""
+    for bits, N, M in ((64, 1024, 4), (64, 64, 3), (32, 1024, 2), (32, 4096, 14), (16, 512, 2)):
+        P, a = _lift_cases(bits, N, M)
+        W = lift_words_per_coeff(P)
+        r = Ref(bits, N, M)
+        ref = r.lift(a, W)
+        assert np.array_equal(crt_lift(a, P), ref), (bits, N, M)
+        assert np.array_equal(crt_unlift(ref, P, DTYPES[bits]), a)
+        assert np.array_equal(r.unlift(ref), a)
+
+
+def test_crt_lift_fixture():
+    k = np.load(os.path.join(GOLDEN, "lift_u64_n64_m3.npz"))
+    P = golden_params(64)["P"][:3]
+    assert np.array_equal(crt_lift(k["polys"], P), k["words"])
+    assert np.array_equal(crt_unlift(k["words"], P, np.uint64), k["polys"])
