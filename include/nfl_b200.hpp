@@ -572,6 +572,9 @@ public:
   void set_non_uniform(uint64_t upper_bound, uint64_t amplifier, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:190-278
     detail::check(nflgpu_non_uniform(ctx(), buf_.p, buf_.count, upper_bound, amplifier, key, first_nonce, nullptr), "nflgpu_non_uniform");
   }
+  void set_hwt(uint32_t hwt, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:355-392
+    detail::check(nflgpu_hwt(ctx(), buf_.p, buf_.count, hwt, key, first_nonce, nullptr), "nflgpu_hwt");
+  }
   void set_zo(uint8_t rho, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:338-349
     detail::check(nflgpu_zo(ctx(), buf_.p, buf_.count, rho, key, first_nonce, nullptr), "nflgpu_zo");
   }

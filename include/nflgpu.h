@@ -158,6 +158,11 @@ int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_
 /* poly::set(nfl::ZO_dist(rho)) (core.hpp:338-349, poly.hpp:59-62): coefficients in {-1, 0, 1} with P(+-1) = (rho/255)/2
  * each, from one keystream byte per coefficient; -1 / +1 are stored as p_cm - 1 / p_cm + 1 exactly as the reference does. */
 int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream);
+/* poly::set(nfl::hwt_dist(hwt)) (core.hpp:355-392, poly.hpp:54-57): exactly `hwt` coefficients are +-1 (p_cm - 1 / p_cm + 1),
+ * chosen by reservoir sampling with rejection-sampled indices.  Each polynomial consumes ceil((degree - hwt) / hwt) + 1
+ * fastrandombytes calls (nonces): polynomial i starts at first_nonce + i * that count, which is the reference's nonce
+ * sequence (an index rejection exactly at a refill boundary, probability < 2^-44 per draw, would shift the reference's). */
+int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce, void *stream);
 
 /* ---- CRT lift: the consumer that needs all residues of a polynomial on one device ------------------------- */
 

@@ -58,6 +58,7 @@ def lib():
         L.nflgpu_uniform.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_non_uniform.argtypes = [vp, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_zo.argtypes = [vp, vp, sz, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64, vp]
+        L.nflgpu_hwt.argtypes = [vp, vp, sz, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_lift_words.argtypes = [vp, ctypes.POINTER(sz)]
         L.nflgpu_poly2mpz.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_mpz2poly.argtypes = [vp, vp, vp, sz, vp]
@@ -172,6 +173,9 @@ class Context:
 
     def non_uniform(self, dst, batch, upper_bound, amplifier, key, first_nonce, stream=0):
         _check(lib().nflgpu_non_uniform(self.h, dst, batch, upper_bound, amplifier, bytes(key), first_nonce, stream))
+
+    def hwt(self, dst, batch, hwt, key, first_nonce, stream=0):
+        _check(lib().nflgpu_hwt(self.h, dst, batch, hwt, bytes(key), first_nonce, stream))
 
     def zo(self, dst, batch, rho, key, first_nonce, stream=0):
         _check(lib().nflgpu_zo(self.h, dst, batch, rho, bytes(key), first_nonce, stream))

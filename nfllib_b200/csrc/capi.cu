@@ -561,6 +561,13 @@ int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_
   return run_sampler(ctx, SAMPLE_NON_UNIFORM, dst, batch, key, first_nonce, upper_bound, amplifier, mask, ctx->degree * ctx->limb_bytes, stream);
 }
 
+int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  if (hwt == 0 || hwt > ctx->degree) { set_error("hwt must be in [1, degree]"); return NFLGPU_ERR_ARG; }  // core.hpp:356
+  const uint64_t calls = (ctx->degree - hwt + hwt - 1) / hwt + 1;  // refills of hwt words + the sign keystream
+  return run_sampler(ctx, SAMPLE_HWT, dst, batch, key, first_nonce, hwt, calls, 0, 64, stream);
+}
+
 int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream) {
   if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
   return run_sampler(ctx, SAMPLE_ZO, dst, batch, key, first_nonce, rho, 0, 0, ctx->degree, stream);

@@ -32,7 +32,7 @@ struct EvArgs {
 cudaError_t launch_eval(int limb_bits, const EvArgs &a, int num_sms, cudaStream_t stream);
 
 // On-device samplers (sampler.cu).
-enum SampleKind { SAMPLE_UNIFORM = 0, SAMPLE_NON_UNIFORM = 1, SAMPLE_ZO = 2 };
+enum SampleKind { SAMPLE_UNIFORM = 0, SAMPLE_NON_UNIFORM = 1, SAMPLE_ZO = 2, SAMPLE_HWT = 3 };
 struct SampleArgs {
   void *dst;
   const uint64_t *moduli;  // [nmoduli], widened
@@ -40,7 +40,7 @@ struct SampleArgs {
   uint64_t first_nonce;
   uint64_t poly_bytes, blocks_per_poly;  // blocks_per_poly = ceil(poly_bytes / 64)
   uint32_t nmoduli, log2_degree, limb_bits, batch;
-  uint64_t param0, param1, param2;  // non_uniform: upper_bound, amplifier, mask;  ZO: rho
+  uint64_t param0, param1, param2;  // non_uniform: upper_bound, amplifier, mask;  ZO: rho;  hwt: hwt, calls per polynomial
 };
 cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream);
 

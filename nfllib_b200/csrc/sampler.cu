@@ -4,6 +4,7 @@
 //   poly::set(uniform const&)              core.hpp:150-187   (mask every limb to the modulus' bit length, one conditional subtract)
 //   poly::set(non_uniform const&)          core.hpp:190-278   (centred bounded noise, same value in every residue)
 //   poly::set(ZO_dist const&)              core.hpp:338-349   ({-1,0,1} from one keystream byte per coefficient)
+//   poly::set(hwt_dist const&)             core.hpp:355-392   (exactly hwt coefficients +-1, reservoir sampling)
 //   nfl::fastrandombytes                    lib/prng/fastrandombytes.cpp:21-34  (Salsa20 keystream, one 64-bit nonce per call)
 //   nfl_crypto_stream_salsa20_amd64_xmm6    lib/prng/*.s       (Salsa20/20, D. J. Bernstein's public specification)
 // Polynomial i of the batch is filled from the keystream (key, first_nonce + i), exactly what `batch` successive
@@ -94,6 +95,50 @@ __global__ void __launch_bounds__(256) zo_kernel(const SampleArgs a) {
   }
 }
 
+// poly::set(hwt_dist) core.hpp:355-392: reservoir sampling is sequential inside a polynomial, so one thread draws one
+// polynomial (the batch supplies the parallelism).  `hit` and `bitmap` are scratch: the reservoir slots and the set of
+// selected positions (the reference sorts the slots; scanning the bitmap in ascending order pairs position and sign word
+// identically).  Polynomial i starts at nonce first_nonce + i * param1, param1 = ceil((N - hwt) / hwt) + 1 calls: exactly the
+// reference's nonce sequence unless an index is rejected right at a refill boundary (probability below 2^-44 per draw).
+__global__ void __launch_bounds__(64) hwt_kernel(const SampleArgs a, uint32_t *hit_all, uint32_t *bitmap_all) {
+  const uint64_t degree = 1ull << a.log2_degree;
+  const uint32_t hwt = (uint32_t)a.param0;
+  const uint64_t poly = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (poly >= a.batch) return;
+  uint32_t *hit = hit_all + poly * hwt;
+  uint32_t *bitmap = bitmap_all + poly * ((degree + 31) / 32);  // zeroed by the launcher
+  uint64_t nonce = a.first_nonce + poly * a.param1, cur = 0, blk = 0;
+  uint32_t x[16], avail = 0, widx = 8;
+  for (uint32_t k = 0; k < hwt; ++k) hit[k] = k;
+  for (uint64_t k = hwt; k < degree; ++k) {
+    const uint64_t reject = 0xffffffffffffffffull / k;
+    uint64_t pos;
+    for (;;) {
+      if (avail == 0) { avail = hwt; cur = nonce++; blk = 0; widx = 8; }
+      if (widx == 8) { salsa20_block(a.key, cur, blk++, x); widx = 0; }
+      pos = ((uint64_t)x[2 * widx + 1] << 32) | x[2 * widx];
+      ++widx; --avail;
+      if (pos <= reject * k) { pos %= k; break; }
+    }
+    if (pos < hwt) hit[pos] = (uint32_t)k;
+  }
+  for (uint32_t k = 0; k < hwt; ++k) atomicOr(&bitmap[hit[k] >> 5], 1u << (hit[k] & 31));
+  cur = nonce; blk = 0; widx = 8;  // the sign keystream: one more fastrandombytes call
+  unsigned char *dst = reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes;  // zeroed by the launcher
+  for (uint64_t wd = 0; wd < (degree + 31) / 32; ++wd) {
+    uint32_t bits = bitmap[wd];
+    while (bits) {
+      const uint32_t bit = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (widx == 8) { salsa20_block(a.key, cur, blk++, x); widx = 0; }
+      const uint32_t sign = x[2 * widx] & 2u;
+      ++widx;
+      for (uint32_t cm = 0; cm < a.nmoduli; ++cm)
+        store_any(dst, a.limb_bits, (uint64_t)cm * degree + wd * 32 + bit, (a.moduli[cm] - 1) + sign);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) uniform_kernel(const SampleArgs a) {
   const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
   for (uint64_t gb = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; gb < total; gb += (uint64_t)gridDim.x * blockDim.x) {
@@ -157,6 +202,21 @@ __global__ void __launch_bounds__(256) uniform_kernel(const SampleArgs a) {
   }
 }
 
+cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream) {
+  if (a.batch == 0) return cudaSuccess;
+  const uint64_t degree = 1ull << a.log2_degree, hwt = a.param0;
+  const size_t hit_bytes = (size_t)a.batch * hwt * 4, bm_bytes = (size_t)a.batch * ((degree + 31) / 32) * 4;
+  unsigned char *scratch = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), hit_bytes + bm_bytes, stream);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(scratch + hit_bytes, 0, bm_bytes, stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(a.dst, 0, (size_t)a.batch * a.poly_bytes, stream)) != cudaSuccess) return e;  // core.hpp:383
+  hwt_kernel<<<(a.batch + 63) / 64, 64, 0, stream>>>(a, reinterpret_cast<uint32_t *>(scratch), reinterpret_cast<uint32_t *>(scratch + hit_bytes));
+  e = cudaGetLastError();
+  cudaFreeAsync(scratch, stream);
+  return e;
+}
+
 cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream) {
   const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
   if (total == 0) return cudaSuccess;
@@ -166,6 +226,7 @@ cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStrea
     case SAMPLE_UNIFORM: uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
     case SAMPLE_NON_UNIFORM: non_uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
     case SAMPLE_ZO: zo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
+    case SAMPLE_HWT: return launch_hwt(a, stream);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

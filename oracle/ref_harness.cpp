@@ -186,8 +186,13 @@ template <class P> static void sample_range(int kind, P *out, size_t batch, unsi
   for (size_t i = 0; i < batch; ++i) {
     if (kind == 0) out[i].set(nfl::uniform());                       // core.hpp:150-187
     else if (kind == 1) out[i].set(nfl::non_uniform(p0, p1));         // core.hpp:190-278
-    else out[i].set(nfl::ZO_dist((uint8_t)p0));                       // core.hpp:338-349
-    ++g_uniform_calls;  // every one of these draws makes exactly one fastrandombytes call
+    else if (kind == 2) out[i].set(nfl::ZO_dist((uint8_t)p0));        // core.hpp:338-349
+    else {                                                            // core.hpp:355-392
+      out[i].set(nfl::hwt_dist((uint32_t)p0));
+      // one fastrandombytes call per refill of hwt words + one for the signs (rejections have probability ~k/2^64: none)
+      g_uniform_calls += (P::degree - p0 + p0 - 1) / p0;
+    }
+    ++g_uniform_calls;  // uniform / non_uniform / ZO: exactly one fastrandombytes call; hwt: the sign call
   }
 }
 #define NFLREF_UNIFORM(T, BITS, N, M) \
@@ -197,7 +202,7 @@ extern "C" {
 // out[0..batch) = successive poly::set(nfl::uniform()) draws; *first_nonce receives the 64-bit nonce the first of
 // them used (one fastrandombytes call, i.e. one nonce, per polynomial).  Single-threaded: the reference's PRNG state
 // is a process-global static.
-// kind: 0 uniform, 1 non_uniform(p0 = upper_bound, p1 = amplifier), 2 ZO_dist(p0 = rho)
+// kind: 0 uniform, 1 non_uniform(p0 = upper_bound, p1 = amplifier), 2 ZO_dist(p0 = rho), 3 hwt_dist(p0 = hwt)
 int nflref_sample(int kind, int limb_bits, size_t degree, size_t nmoduli, void *out, size_t batch, unsigned long long p0,
                   unsigned long long p1, unsigned long long *first_nonce) {
   if (reinterpret_cast<uintptr_t>(out) & 31) return -2;

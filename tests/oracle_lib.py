@@ -58,6 +58,8 @@ class Oracle:
             L.nflo_uniform.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint64]
             L.nflo_non_uniform.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64]
             L.nflo_zo.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64]
+            L.nflo_hwt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64,
+                                   ctypes.POINTER(ctypes.c_uint64)]
             cls._lib = L
         return cls._lib
 
@@ -98,6 +100,14 @@ class Oracle:
         out = np.empty((batch, self.M, self.N), dtype=self.dtype)
         self.lib().nflo_non_uniform(self.h, out.ctypes.data, batch, upper_bound, amplifier, bytes(key), first_nonce)
         return out
+
+    def hwt(self, batch, hwt, key, first_nonce):
+        """(polys, number of fastrandombytes calls made)"""
+        out = np.empty((batch, self.M, self.N), dtype=self.dtype)
+        calls = ctypes.c_uint64()
+        rc = self.lib().nflo_hwt(self.h, out.ctypes.data, batch, hwt, bytes(key), first_nonce, ctypes.byref(calls))
+        assert rc == 0
+        return out, calls.value
 
     def zo(self, batch, rho, key, first_nonce):
         out = np.empty((batch, self.M, self.N), dtype=self.dtype)
@@ -156,7 +166,7 @@ class Ref:
         n = ctypes.c_ulonglong()
         self.lib().nflref_sample.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                              ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]
-        rc = self.lib().nflref_sample({"uniform": 0, "non_uniform": 1, "zo": 2}[kind], self.bits, self.N, self.M, out.ctypes.data, batch, p0, p1,
+        rc = self.lib().nflref_sample({"uniform": 0, "non_uniform": 1, "zo": 2, "hwt": 3}[kind], self.bits, self.N, self.M, out.ctypes.data, batch, p0, p1,
                                       ctypes.byref(n))
         assert rc == 0, rc
         return n.value, out

@@ -368,3 +368,33 @@ def test_crt_lift_matches_oracle_and_reference():
         c.free(dp); c.free(back)
     with pytest.raises(nb.NflGpuError):
         ctx_for(64, 64, 17).lift_words()   # 17 * 62 bits > 1024
+
+
+def test_hwt_sampler():
+    """nflgpu_hwt vs the oracle restatement of core.hpp:355-392 (pinned against the reference in tests/test_oracle.py) and the
+    live reference when it travelled."""
+    key = bytes(range(1, 33))
+    for bits, N, M in ((64, 1024, 4), (32, 8, 2), (16, 512, 2), (64, 64, 3)):
+        c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+        for hwt in (1, 3, N // 4, N - 1, N):
+            batch = 5
+            d = c.alloc(batch)
+            c.hwt(d, batch, hwt, key, 1000)
+            got = np.empty((batch, M, N), c.dtype)
+            c.download(got, d, batch); c.sync()
+            c.free(d)
+            exp, calls = o.hwt(batch, hwt, key, 1000)
+            assert np.array_equal(got, exp), (bits, N, M, hwt)
+            assert all(np.count_nonzero(got[b, 0]) == hwt for b in range(batch))
+        with pytest.raises(nb.NflGpuError):
+            c.hwt(1, 1, N + 1, key, 0)
+    if have_ref():
+        bits, N, M = 64, 1024, 4
+        n0, ref = Ref(bits, N, M).sample("hwt", 3, 64)
+        c = ctx_for(bits, N, M)
+        d = c.alloc(3)
+        c.hwt(d, 3, 64, Ref.FIXED_KEY, n0)
+        got = np.empty((3, M, N), c.dtype)
+        c.download(got, d, 3); c.sync()
+        c.free(d)
+        assert np.array_equal(got, ref)

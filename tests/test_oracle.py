@@ -138,6 +138,18 @@ def test_oracle_bounded_and_zo_samplers_match_live_reference():
             assert np.array_equal(o.zo(3, rho, Ref.FIXED_KEY, n0), ref), (bits, N, M, rho)
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so not built (needs /root/reference)")
+def test_oracle_hwt_sampler_matches_live_reference():
+    for bits, N, M in ((64, 1024, 4), (32, 8, 2), (16, 512, 2), (64, 64, 3)):
+        r, o = Ref(bits, N, M), Oracle(bits, N, M)
+        for hwt in (1, 3, N // 4, N - 1, N):
+            n0, ref = r.sample("hwt", 2, hwt)
+            mine, calls = o.hwt(2, hwt, Ref.FIXED_KEY, n0)
+            assert np.array_equal(mine, ref), (bits, N, M, hwt)
+            assert calls == 2 * ((N - hwt + hwt - 1) // hwt + 1)
+            assert all(np.count_nonzero(mine[b, 0]) == hwt for b in range(2))
+
+
 def test_oracle_uniform_sampler_fixture():
     k = np.load(os.path.join(GOLDEN, "uniform_u64_n1024_m4.npz"))
     o = Oracle(64, 1024, 4)
