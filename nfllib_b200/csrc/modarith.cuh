@@ -20,8 +20,9 @@ template <> struct Arith<64> {
   static constexpr int WORD_BITS = 64;
   static __device__ __forceinline__ Word tw_w(const TW &t) { return t.x; }
   static __device__ __forceinline__ Word tw_ws(const TW &t) { return t.y; }
-  // (measured, profiles/r01b_*: on sm_100 IMAD.WIDE.U32 holds the fmaheavy pipe 4 cycles per warp, IMAD.HI.U32 ~6 and a
-  //  plain IMAD 2, so the four IMAD.WIDE of __umul64hi are cheaper than any formulation using IMAD.HI.)
+  // (measured, profiles/r01_integer_pipe_model.md: integer code on sm_100 costs ~2 issue cycles per IMAD / IMAD.WIDE /
+  //  IADD3-class instruction and about twice that per IMAD.HI, so the four IMAD.WIDE of __umul64hi beat any formulation
+  //  built on IMAD.HI.)
   static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umul64hi(a, b); }
   // y*w - floor(y*ws / 2^64)*p  in [0, 2p) for any 64-bit y  (algos.hpp:37-38).  `np` is -p mod 2^64 (kept opaque
   // to the optimiser by the caller) so the whole right-hand side is one multiply-accumulate chain, no subtraction.
@@ -38,7 +39,7 @@ template <> struct Arith<32> {
   static constexpr int WORD_BITS = 32;
   static __device__ __forceinline__ Word tw_w(const TW &t) { return t.x; }
   static __device__ __forceinline__ Word tw_ws(const TW &t) { return t.y; }
-  // hi32(a*b) through IMAD.WIDE (4 pipe cycles) instead of the IMAD.HI (~6) that __umulhi compiles to
+  // hi32(a*b) through IMAD.WIDE instead of the IMAD.HI (about two issue slots) that __umulhi compiles to
   static __device__ __forceinline__ Word mulhi(Word a, Word b) {
     Word hi;
     asm("{\n\t.reg .b64 t;\n\t.reg .b32 lo;\n\tmul.wide.u32 t, %1, %2;\n\tmov.b64 {lo, %0}, t;\n\t}" : "=r"(hi) : "r"(a), "r"(b));

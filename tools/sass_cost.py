@@ -1,6 +1,7 @@
-"""Static pipe-cycle model of a kernel from its SASS (development aid, no GPU needed).
-Model calibrated on the r01a ncu capture of ntt_fwd_kernel<64,10> (profiles/r01a_*): per warp-instruction and SM sub-partition,
-IMAD.WIDE* occupies the fmaheavy pipe 4 cycles, IMAD.HI ~6 (fitted on r01b captures), every other IMAD* 2 cycles, ALU-pipe instructions 2 cycles, 1 issue slot each.
+"""Static cost model of a kernel from its SASS (development aid, no GPU needed).
+Integer code on sm_100 is issue-bound (profiles/r01_integer_pipe_model.md): ~2 cycles per IMAD / IMAD.WIDE / IADD3-class warp
+instruction and sub-partition, IMAD.HI about twice that; `issue_cyc` (the instruction count of the hot loop) is the figure that
+tracks measured time.  The fmaheavy / alu columns reproduce ncu's pipe-busy counters (IMAD.WIDE = 4 busy cycles, IMAD = 2, ALU = 2).
 usage: python tools/sass_cost.py <object-or-so> <kernel-name-substring> [butterflies]"""
 import re
 import subprocess
