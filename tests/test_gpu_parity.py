@@ -398,3 +398,9 @@ def test_hwt_sampler():
         c.download(got, d, 3); c.sync()
         c.free(d)
         assert np.array_equal(got, ref)
+
+
+def test_graft_entry_smoke():
+    """The driver's smoke() entry point itself."""
+    import __graft_entry__
+    __graft_entry__.smoke()
