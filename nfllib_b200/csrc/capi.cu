@@ -7,6 +7,7 @@
 #include "pointwise.h"
 
 #include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -71,6 +72,7 @@ struct nflgpu_ctx {
   void *d_tw_raw_fwd = nullptr, *d_tw_raw_inv = nullptr;  // cyclic (no-twist) tables, built on first use
   std::vector<uint64_t> roots;
   uint64_t kmax = 0;
+  std::mutex lazy_mu;  // guards the build-on-first-use tables below (raw twiddles, CRT lift)
   // CRT-lift tables, built on first use (lift.cu)
   int lift_words = 0;
   uint64_t *d_lift = nullptr;  // [inv | c64 | qhat (M*W) | q (W)]
@@ -140,9 +142,14 @@ int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch,
   if (batch == 0) return NFLGPU_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
-  if (raw && !ctx->d_tw_raw_fwd) {  // first use of the cyclic transform on this context
-    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    if (int rc2 = upload_tables(ctx, true, &ctx->d_tw_raw_fwd, &ctx->d_tw_raw_inv)) return rc2;
+  if (raw) {  // first use of the cyclic transform on this context builds its tables
+    std::lock_guard<std::mutex> lock(ctx->lazy_mu);
+    if (!ctx->d_tw_raw_fwd) {
+      void *f = nullptr, *v = nullptr;
+      if (int rc2 = upload_tables(ctx, true, &f, &v)) return rc2;
+      ctx->d_tw_raw_inv = v;
+      ctx->d_tw_raw_fwd = f;
+    }
   }
   NttLaunch l;
   l.src = src; l.dst = dst; l.moduli = ctx->d_moduli_word;
@@ -462,6 +469,7 @@ size_t big_bits(const Big &a) {
 }
 // moduli product, Q/p_cm, their inverses (gmp.hpp:116-150) -> device
 int ensure_lift_tables(nflgpu_ctx *ctx) {
+  std::lock_guard<std::mutex> lock(ctx->lazy_mu);
   if (ctx->d_lift) return NFLGPU_OK;
   const size_t M = ctx->nmoduli;
   Big Q(1, 1);

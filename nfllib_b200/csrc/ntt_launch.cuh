@@ -31,6 +31,7 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
   else if constexpr (MODE == 2) kernel = ntt_fwd_kernel<LB, LOGN, true>;
   else kernel = ntt_fwd_kernel<LB, LOGN, false>;
   // per-device one-time setup: opt in to the shared-memory size and ask the occupancy calculator
+  // (racing first calls from two host threads would both compute the same value; the store is a plain int)
   static int blocks_per_sm[64] = {0};
   if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
   if (blocks_per_sm[device] == 0) {
