@@ -20,16 +20,19 @@
 #define NFL_B200_HPP
 
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 #include <iostream>
 #include <iterator>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <new>
-#include <random>
 #include <stdexcept>
 #include <string>
 #include <tuple>
@@ -115,10 +118,46 @@ template <class T> constexpr unsigned int params<T>::kMaxPolyDegree;
 namespace simd { struct cuda {}; }
 #define CC_SIMD nfl::simd::cuda
 
-struct uniform {};  // poly.hpp:42 — test-grade here (std::mt19937_64), NOT the reference's Salsa20 stream
+/* Generators to initialise random polynomials (poly.hpp:42-62).  All four are drawn ON THE DEVICE by the samplers of
+ * libnflgpu (nflgpu_uniform / non_uniform / zo / hwt), which follow the reference's algorithms over the same Salsa20/20
+ * keystream (core.hpp:150-392, lib/prng/fastrandombytes.cpp:21-34); like the reference, the process keys itself once
+ * from /dev/urandom and uses a 64-bit nonce counter. */
+struct uniform {};
+struct non_uniform {
+  uint64_t upper_bound;
+  uint64_t amplifier;
+  non_uniform(uint64_t ub) : upper_bound(ub), amplifier(1) {}
+  non_uniform(uint64_t ub, uint64_t amp) : upper_bound(ub), amplifier(amp) {}
+};
+struct hwt_dist {  // hamming weight distribution
+  uint32_t hwt;
+  hwt_dist(uint32_t hwt_) : hwt(hwt_) {}
+};
+struct ZO_dist {  // P(1) = P(-1) = (rho/0xFF)/2, P(0) = 1 - P(1) - P(-1)
+  uint8_t rho;
+  ZO_dist(uint8_t rho_ = 0x7F) : rho(rho_) {}
+};
+
+namespace detail {
+struct prng_state {  // lib/prng/fastrandombytes.cpp:17-34: key from the OS once, nonce counter from 0
+  uint8_t key[32];
+  std::atomic<uint64_t> nonce;
+  prng_state() : nonce(0) {
+    FILE *f = std::fopen("/dev/urandom", "rb");
+    const bool ok = f && std::fread(key, 1, sizeof(key), f) == sizeof(key);
+    if (f) std::fclose(f);
+    if (!ok) throw std::runtime_error("nfl_b200: cannot read /dev/urandom");
+  }
+  static prng_state &get() { static prng_state s; return s; }
+  uint64_t take(uint64_t count) { return nonce.fetch_add(count); }
+};
+}  // namespace detail
 
 template <class T, size_t Degree, size_t NbModuli> class poly;
 template <class T, size_t Degree, size_t NbModuli> class poly_p;
+
+// proxy the reference's tests use to reach poly's protected members (poly.hpp:71-76,85,202; tests/ntt_perfs.cpp:122-134)
+namespace tests { template <class P> class poly_tests_proxy; }
 
 // ---------------------------------------------------------------------------------------------------------
 // Backend: one nflgpu context per (T, Degree, NbModuli), created on first use (the reference builds its
@@ -138,6 +177,24 @@ template <class T, size_t Degree, size_t NbModuli> struct backend {
   }
   ~backend() { nflgpu_ctx_destroy(ctx); }
   static backend &get() { static backend b; return b; }
+};
+
+// One single-residue context per modulus index, for the per-residue statics core::ntt / core::inv_ntt (core.hpp:455-557)
+template <class T, size_t Degree> struct residue_backend {
+  std::mutex mu;
+  std::map<size_t, nflgpu_ctx *> ctxs;
+  ~residue_backend() { for (auto &kv : ctxs) nflgpu_ctx_destroy(kv.second); }
+  static residue_backend &get() { static residue_backend b; return b; }
+  nflgpu_ctx *ctx(size_t cm) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = ctxs.find(cm);
+    if (it != ctxs.end()) return it->second;
+    const char *dev = std::getenv("NFL_B200_DEVICE");
+    nflgpu_ctx *c = nullptr;
+    check(nflgpu_ctx_create(&c, limb_traits<T>::bits, Degree, 1, cm, dev ? std::atoi(dev) : 0, nullptr, nullptr), "nflgpu_ctx_create");
+    ctxs[cm] = c;
+    return c;
+  }
 };
 
 // RAII device buffer of `count` polys
@@ -166,8 +223,9 @@ template <class Op, class... Args> struct expr {
   typedef typename first_arg::poly_type poly_type;
   std::tuple<Args const &...> args;
   explicit expr(Args const &... a) : args(a...) {}
-  // the reference's semantics: `==` is true iff ANY coefficient is equal, `!=` iff ANY differs (ops.hpp:81-95)
-  explicit operator bool() const;
+  // the reference's semantics: `==` is true iff ANY coefficient is equal, `!=` iff ANY differs (ops.hpp:81-95);
+  // implicit like the reference's, so `ret &= (a == b)` and `bool ok = (a == b)` compile (tests/poly_p.cpp:22)
+  operator bool() const;
 };
 
 }  // namespace ops
@@ -313,6 +371,8 @@ template <class Op, class... A> struct is_operand<ops::expr<Op, A...>> : std::tr
 // poly  (poly.hpp:82-309)
 // ---------------------------------------------------------------------------------------------------------
 template <class T, size_t Degree, size_t NbModuli> class poly {
+  template <class P> friend class tests::poly_tests_proxy;
+
   static constexpr size_t N = Degree * NbModuli;
   T _data[N] __attribute__((aligned(32)));
 
@@ -335,6 +395,9 @@ public:
   /* constructors (core.hpp:64-147) */
   poly() { set(value_type(0)); }
   poly(uniform const &mode) { set(mode); }
+  poly(non_uniform const &mode) { set(mode); }
+  poly(hwt_dist const &mode) { set(mode); }
+  poly(ZO_dist const &mode) { set(mode); }
   poly(value_type v, bool reduce_coeffs = true) { set(v, reduce_coeffs); }
   poly(std::initializer_list<value_type> values, bool reduce_coeffs = true) { set(values.begin(), values.end(), reduce_coeffs); }
   template <class It> poly(It first, It last, bool reduce_coeffs = true) { set(first, last, reduce_coeffs); }
@@ -363,20 +426,50 @@ public:
       for (; i < degree; ++i) _data[cm * degree + i] = 0;
     }
   }
+  /* random fills (core.hpp:150-392): one device sampler launch + download per call */
   void set(uniform const &) {
-    static std::mt19937_64 gen((std::random_device())());
-    for (size_t cm = 0; cm < nmoduli; ++cm)
-      for (size_t i = 0; i < degree; ++i) _data[cm * degree + i] = static_cast<T>(gen() % get_modulus(cm));
+    detail::prng_state &g = detail::prng_state::get();
+    detail::dev_buf<poly> b(1);
+    detail::check(nflgpu_uniform(backend_type::get().ctx, b.p, 1, g.key, g.take(1), nullptr), "nflgpu_uniform");
+    fetch(b);
+  }
+  void set(non_uniform const &mode) {
+    if (mode.upper_bound >= get_modulus(0))  // core.hpp:201-206
+      throw std::runtime_error("set(non_uniform): upper_bound is larger than the modulus");
+    detail::prng_state &g = detail::prng_state::get();
+    detail::dev_buf<poly> b(1);
+    detail::check(nflgpu_non_uniform(backend_type::get().ctx, b.p, 1, mode.upper_bound, mode.amplifier, g.key, g.take(1), nullptr),
+                  "nflgpu_non_uniform");
+    fetch(b);
+  }
+  void set(hwt_dist const &mode) {
+    detail::prng_state &g = detail::prng_state::get();
+    detail::dev_buf<poly> b(1);
+    const uint64_t refills = mode.hwt ? (degree - mode.hwt + mode.hwt - 1) / mode.hwt + 1 : 1;  // nonces one draw consumes (nflgpu.h)
+    detail::check(nflgpu_hwt(backend_type::get().ctx, b.p, 1, mode.hwt, g.key, g.take(refills), nullptr), "nflgpu_hwt");
+    fetch(b);
+  }
+  void set(ZO_dist const &mode) {
+    detail::prng_state &g = detail::prng_state::get();
+    detail::dev_buf<poly> b(1);
+    detail::check(nflgpu_zo(backend_type::get().ctx, b.p, 1, mode.rho, g.key, g.take(1), nullptr), "nflgpu_zo");
+    fetch(b);
   }
 
   /* assignment */
   poly &operator=(value_type v) { set(v); return *this; }
   poly &operator=(uniform const &mode) { set(mode); return *this; }
+  poly &operator=(non_uniform const &mode) { set(mode); return *this; }
+  poly &operator=(hwt_dist const &mode) { set(mode); return *this; }
+  poly &operator=(ZO_dist const &mode) { set(mode); return *this; }
   poly &operator=(std::initializer_list<value_type> values) { set(values); return *this; }
   template <class Op, class... Args> poly &operator=(ops::expr<Op, Args...> const &e) {  // core.hpp:24-37
     detail::assign_expr<poly, ops::expr<Op, Args...>>(*this, e);
     return *this;
   }
+
+  /* conversion (poly.hpp:138, core.hpp:39-43): true iff some coefficient is nonzero */
+  explicit operator bool() const { return std::find_if(begin(), end(), [](value_type v) { return v != 0; }) != end(); }
 
   /* iterators, indexing, misc (poly.hpp:141-163) */
   iterator begin() { return _data; }
@@ -398,7 +491,95 @@ public:
   /* manual serializers (poly.hpp:180-185): identical byte layout */
   void serialize_manually(std::ostream &os) { os.write(reinterpret_cast<char *>(_data), N * sizeof(T)); }
   void deserialize_manually(std::istream &is) { is.read(reinterpret_cast<char *>(_data), N * sizeof(T)); }
+  /* serializer (cereal, poly.hpp:187-191) */
+  template <class Archive> void serialize(Archive &archive) { archive(_data); }
+
+private:
+  void fetch(detail::dev_buf<poly> const &b) {
+    detail::check(nflgpu_download(backend_type::get().ctx, _data, b.p, 1, nullptr), "nflgpu_download");
+    detail::check(nflgpu_sync(backend_type::get().ctx, nullptr), "nflgpu_sync");
+  }
+
+protected:
+  /* poly::core (poly.hpp:195-238): the per-residue statics and the reference's host-visible tables, kept so code that
+   * reaches them through tests::poly_tests_proxy (tests/ntt_perfs.cpp:122-134) compiles unchanged.  The device kernels
+   * use their own merged-psi tables (csrc/tables.cpp); these copies follow core::initialize / prep_wtab
+   * (core.hpp:564-581,625-686) value for value and exist only when `base` is referenced. */
+  class core {
+    template <class P> friend class tests::poly_tests_proxy;
+
+  public:
+    core() { initialize(); }
+    void ntt_pow_phi(poly &op) { op.ntt_pow_phi(); }
+    void invntt_pow_invphi(poly &op) { op.invntt_pow_invphi(); }
+    // core.hpp:455-532 — cyclic transform of ONE residue, in place, canonical in and out; always returns true
+    // (core.hpp:531).  Runs on the device (nflgpu_ntt_raw_fwd); `wtab` must be this class's own table of the
+    // residue with modulus p (the device tables are derived from the same omega), anything else throws.
+    static bool ntt(value_type *x, const value_type *wtab, const value_type *winvtab, value_type const p) {
+      if (degree == 1) return true;
+      const size_t cm = residue_of(p);
+      if (wtab != base.omegas[cm] || winvtab != base.shoupomegas[cm])
+        throw std::runtime_error("nfl_b200: core::ntt runs with the library's own omega tables only");
+      detail::check(nflgpu_host_op(detail::residue_backend<T, Degree>::get().ctx(cm), 10, x, x, nullptr, nullptr, 1), "core::ntt");
+      return true;
+    }
+    // core.hpp:539-557 — bit-reverse, core::ntt with omega^-1, bit-reverse; invK is unused there as well
+    static bool inv_ntt(value_type *x, const value_type *inv_wtab, const value_type *inv_winvtab, value_type, value_type const p) {
+      if (degree == 1) return true;
+      const size_t cm = residue_of(p);
+      if (inv_wtab != base.invomegas[cm] || inv_winvtab != base.shoupinvomegas[cm])
+        throw std::runtime_error("nfl_b200: core::inv_ntt runs with the library's own omega^-1 tables only");
+      detail::check(nflgpu_host_op(detail::residue_backend<T, Degree>::get().ctx(cm), 11, x, x, nullptr, nullptr, 1), "core::inv_ntt");
+      return true;
+    }
+
+  private:
+    value_type phis[nmoduli][degree] __attribute__((aligned(32))), shoupphis[nmoduli][degree] __attribute__((aligned(32))),
+        invpoly_times_invphis[nmoduli][degree] __attribute__((aligned(32))),
+        shoupinvpoly_times_invphis[nmoduli][degree] __attribute__((aligned(32))), omegas[nmoduli][degree * 2] __attribute__((aligned(32))),
+        *shoupomegas[nmoduli], invomegas[nmoduli][2 * degree] __attribute__((aligned(32))), *shoupinvomegas[nmoduli], invpolyDegree[nmoduli];
+
+    static size_t residue_of(value_type p) {
+      for (size_t cm = 0; cm < nmoduli; ++cm)
+        if (get_modulus(cm) == p) return cm;
+      throw std::runtime_error("nfl_b200: modulus is not one of this poly type's moduli");
+    }
+    static value_type mulm(value_type a, value_type b, value_type p) { return static_cast<value_type>((static_cast<unsigned __int128>(a) * b) % p); }
+    static value_type shoupv(value_type v, value_type p) {  // floor(v * 2^w / p), core.hpp:575
+      return static_cast<value_type>((static_cast<unsigned __int128>(v) << params<T>::kModulusRepresentationBitsize) / p);
+    }
+    static void prep_wtab(value_type *wtab, value_type *wtabshoup, value_type w, value_type p) {  // core.hpp:564-581
+      for (size_t K = degree; K >= 2; K /= 2) {
+        value_type wi = 1;
+        for (size_t i = 0; i < K / 2; ++i) { *wtab++ = wi; *wtabshoup++ = shoupv(wi, p); wi = mulm(wi, w, p); }
+        w = mulm(w, w, p);
+      }
+    }
+    void initialize() {  // core.hpp:625-686
+      for (size_t cm = 0; cm < nmoduli; ++cm) {
+        const value_type p = get_modulus(cm);
+        shoupomegas[cm] = omegas[cm] + degree;
+        shoupinvomegas[cm] = invomegas[cm] + degree;
+        value_type phi = params<T>::primitive_roots[cm];
+        for (size_t d = degree; d < params<T>::kMaxPolyDegree; d *= 2) phi = mulm(phi, phi, p);
+        value_type t = 1;
+        for (size_t i = 0; i < degree; ++i) { phis[cm][i] = t; shoupphis[cm][i] = shoupv(t, p); t = mulm(t, phi, p); }
+        const value_type invphi = mulm(t, phis[cm][degree - 1], p);  // phi^degree * phi^(degree-1) = phi^-1
+        invpolyDegree[cm] = mulm(params<T>::invkMaxPolyDegree[cm], static_cast<value_type>(params<T>::kMaxPolyDegree / degree), p);
+        t = invpolyDegree[cm];
+        for (size_t i = 0; i < degree; ++i) {
+          invpoly_times_invphis[cm][i] = t; shoupinvpoly_times_invphis[cm][i] = shoupv(t, p); t = mulm(t, invphi, p);
+        }
+        prep_wtab(omegas[cm], shoupomegas[cm], mulm(phi, phi, p), p);
+        prep_wtab(invomegas[cm], shoupinvomegas[cm], mulm(invphi, invphi, p), p);
+      }
+    }
+  } __attribute__((aligned(32)));
+
+  static core base;
 } __attribute__((aligned(32)));
+
+template <class T, size_t D, size_t M> typename poly<T, D, M>::core poly<T, D, M>::base;
 
 template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::degree;
 template <class T, size_t D, size_t M> constexpr size_t poly<T, D, M>::nmoduli;
@@ -437,7 +618,6 @@ public:
   poly_p(poly_p const &o) : p_(o.p_) {}
   poly_p(poly_p &o) : p_(o.p_) {}
   poly_p(poly_p &&o) : p_(std::move(o.p_)) {}
-  poly_p(std::initializer_list<value_type> values) : p_(make(values)) {}
   template <class A0, class... Args> poly_p(A0 &&a0, Args &&... args) : p_(make(std::forward<A0>(a0), std::forward<Args>(args)...)) {}
 
   poly_type &poly_obj() { detach(); return *p_; }
@@ -461,6 +641,7 @@ public:
   template <class... Args> void set(Args &&... args) { poly_obj().set(std::forward<Args>(args)...); }
   void serialize_manually(std::ostream &os) { poly_obj().serialize_manually(os); }
   void deserialize_manually(std::istream &is) { poly_obj().deserialize_manually(is); }
+  template <class Archive> void serialize(Archive &archive) { archive(poly_obj()); }
 };
 template <class T, size_t D, size_t M> constexpr size_t poly_p<T, D, M>::degree;
 template <class T, size_t D, size_t M> constexpr size_t poly_p<T, D, M>::nmoduli;
@@ -536,11 +717,15 @@ template <class T, size_t D, size_t M> void mul(poly<T, D, M> &out, poly<T, D, M
 template <class T, size_t Degree, size_t AggregatedModulusBitSize>
 using poly_from_modulus = poly<T, Degree, AggregatedModulusBitSize / params<T>::kModulusBitsize>;
 
-/* stream operator (core.hpp:398-421): "{ c0U, c1U, ... }" per residue */
+/* stream operator (core.hpp:397-421): "{ c0ULL, c1ULL, ... }" over all residues, literal suffix by limb type */
 template <class T, size_t D, size_t M> std::ostream &operator<<(std::ostream &os, poly<T, D, M> const &p) {
+  const char *term = sizeof(T) == 8 ? "ULL" : sizeof(T) == 4 ? "UL" : "U";
   os << "{ ";
-  for (size_t i = 0; i < D * M; ++i) os << (i ? ", " : "") << static_cast<uint64_t>(p.begin()[i]) << "U";
+  for (size_t i = 0; i < D * M; ++i) os << (i ? ", " : "") << p.begin()[i] << term;
   return os << " }";
+}
+template <class T, size_t D, size_t M> std::ostream &operator<<(std::ostream &os, poly_p<T, D, M> const &p) {  // poly_p.hpp:213-217
+  return os << p.poly_obj();
 }
 
 // ---------------------------------------------------------------------------------------------------------

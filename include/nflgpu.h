@@ -179,7 +179,7 @@ int nflgpu_mpz2poly(nflgpu_ctx *ctx, void *dst_polys, const uint64_t *src_words,
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked
  * and double-buffered over two streams.  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,
- * 6 sub, 8 polymul, 9 muladd.  Unused operands are NULL.  These are the calls bench.py's e2e figure times.
+ * 6 sub, 8 polymul, 9 muladd, 10 raw_fwd (core::ntt), 11 raw_inv (core::inv_ntt).  Unused operands are NULL.  These are the calls bench.py's e2e figure times.
  * Not re-entrant per context (the staging buffers belong to the context): serialise calls on one context, or use
  * one context per host thread. */
 int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host,

@@ -77,6 +77,11 @@ struct nflgpu_ctx {
   int lift_words = 0;
   uint64_t *d_lift = nullptr;  // [inv | c64 | qhat (M*W) | q (W)]
   std::atomic<uint64_t> launches{0};
+  // dynamic unit scheduling of the NTT kernels: kSchedSlots independent sets of nmoduli + 1 counters, used round-robin so
+  // launches in flight on different streams never share one (each launch leaves its set zeroed again)
+  static constexpr uint64_t kSchedSlots = 256;
+  uint32_t *d_sched = nullptr;
+  std::atomic<uint64_t> sched_seq{0};
   static constexpr int kStages = 4;
   HostStage stage[kStages];
   size_t stage_polys = 0;  // capacity of every staging buffer, in polynomials
@@ -156,6 +161,7 @@ int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch,
   l.tw = raw ? (mode == 1 ? ctx->d_tw_raw_inv : ctx->d_tw_raw_fwd) : (mode == 1 ? ctx->d_tw_inv : ctx->d_tw_fwd);
   l.nmoduli = (uint32_t)ctx->nmoduli; l.batch = (uint32_t)batch;
   l.other = other; l.consts = ctx->d_consts;
+  l.sched = ctx->d_sched + (ctx->sched_seq.fetch_add(1) % nflgpu_ctx::kSchedSlots) * (ctx->nmoduli + 1);
   CUDA_TRY(launch_ntt(ctx->limb_bits, ctx->log2_degree, mode, l, ctx->device, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return NFLGPU_OK;
@@ -299,6 +305,8 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
   CTX_TRY(cudaMemcpy(ctx->d_moduli_word, words.data(), words.size(), cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_moduli64, ctx->moduli.data(), nmoduli * 8, cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_consts, consts.data(), nmoduli * 8, cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->d_sched), nflgpu_ctx::kSchedSlots * (nmoduli + 1) * sizeof(uint32_t)));
+  CTX_TRY(cudaMemset(ctx->d_sched, 0, nflgpu_ctx::kSchedSlots * (nmoduli + 1) * sizeof(uint32_t)));
 #undef CTX_TRY
   *out = ctx;
   return NFLGPU_OK;
@@ -312,7 +320,7 @@ int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
     for (int i = 0; i < 4; ++i) { if (s.dev[i]) cudaFree(s.dev[i]); if (s.pin[i]) cudaFreeHost(s.pin[i]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
+  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts); cudaFree(ctx->d_sched);
   delete ctx;
   return NFLGPU_OK;
 }
@@ -612,7 +620,7 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   if (!ctx || !dst_host || !a_host) { set_error("null argument"); return NFLGPU_ERR_ARG; }
   int nin;
   switch (op) {
-    case 0: case 1: case 4: nin = 1; break;
+    case 0: case 1: case 4: case 10: case 11: nin = 1; break;
     case 2: case 5: case 6: case 8: nin = 2; break;
     case 3: case 9: nin = 3; break;
     default: set_error("unknown op"); return NFLGPU_ERR_ARG;
@@ -650,6 +658,8 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
         case 6: rc = nflgpu_sub(ctx, dp[3], dp[0], dp[1], batch, st); break;
         case 8: rc = nflgpu_polymul(ctx, dp[3], dp[0], dp[1], batch, st); break;
         case 9: rc = nflgpu_muladd(ctx, dp[3], dp[0], dp[1], dp[2], batch, st); break;
+        case 10: rc = nflgpu_ntt_raw_fwd(ctx, dp[3], dp[0], batch, st); break;
+        case 11: rc = nflgpu_ntt_raw_inv(ctx, dp[3], dp[0], batch, st); break;
       }
       if (rc != NFLGPU_OK) return rc;
       CUDA_TRY(cudaStreamSynchronize(ctx->stage[0].stream));
@@ -711,6 +721,8 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
       case 6: rc = nflgpu_sub(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
       case 8: rc = nflgpu_polymul(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
       case 9: rc = nflgpu_muladd(ctx, s.dev[3], s.dev[0], s.dev[1], s.dev[2], cnt, st); break;
+      case 10: rc = nflgpu_ntt_raw_fwd(ctx, s.dev[3], s.dev[0], cnt, st); break;
+      case 11: rc = nflgpu_ntt_raw_inv(ctx, s.dev[3], s.dev[0], cnt, st); break;
     }
     if (rc != NFLGPU_OK) break;
     char *out = static_cast<char *>(dst_host) + done * poly_bytes;

@@ -14,6 +14,7 @@ struct NttLaunch {
   uint32_t nmoduli, batch;
   const void *other = nullptr;        // fused epilogue operand (mode 2 only)
   const uint64_t *consts = nullptr;   // Barrett constants (mode 2 only)
+  uint32_t *sched = nullptr;  // nmoduli + 1 zeroed counters for this launch (dynamic unit scheduling)
 };
 
 // Returns cudaErrorInvalidValue when (limb_bits, log2_degree) has no kernel.

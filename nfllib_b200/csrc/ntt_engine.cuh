@@ -37,6 +37,9 @@ struct NttArgs {
   // fused epilogue of the forward kernel (nflgpu_polymul): dst = ntt_pow_phi(src) * other, coefficient-wise
   const void *other;       // Store[batch][nmoduli][N], canonical, NTT domain; null when unused
   const uint64_t *consts;  // Barrett constants per residue (pointwise.h)
+  // dynamic unit scheduling (NttCfg::DYNAMIC): sched[cm] = next unclaimed sub-block of residue cm, sched[nmoduli] = CTAs done;
+  // all zero between launches (the last CTA to finish resets them)
+  uint32_t *sched;
 };
 
 template <int LB, int LOGN> struct NttCfg {
@@ -74,9 +77,23 @@ template <int LB, int LOGN> struct NttCfg {
 #endif
   static constexpr bool TW_SMEM = SPLIT == 0 && (size_t)N * sizeof(TW) <= 32768;
   static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)N * sizeof(TW) : 0;
-  static constexpr size_t SMEM_BYTES = TW_BYTES + 16 /* mbarrier */ + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
+  // Unit slots claim their next sub-block from a per-residue atomic counter instead of striding over the batch: a slot
+  // that runs ahead (the warp schedulers are not fair) takes more units, so all resident warps stay busy until the batch
+  // is exhausted (static striding left the average warp idle for the last ~20 % of the launch, ncu sm__warps_active).
+#ifdef NFLGPU_DYNAMIC
+  static constexpr bool DYNAMIC = NFLGPU_DYNAMIC != 0;
+  static constexpr bool CLAIM_LATE = NFLGPU_DYNAMIC == 2;  // claim at the bottom of the iteration (no register carried through the unit)
+#else
+  static constexpr bool DYNAMIC = true;
+  static constexpr bool CLAIM_LATE = false;
+#endif
+  static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
+  static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
+  static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
   // tile address of a position (only its offset inside the sub-block matters)
   static __device__ __forceinline__ int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
+  // the same for a compile-time position offset made of register-index bits only (below B by construction)
+  static __host__ __device__ constexpr int pad_k(int off) { return off + (off >> e) * PADW; }
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------
@@ -202,8 +219,11 @@ template <class C, int PASS> __device__ __forceinline__ void tile_load(typename 
       for (int j = 0; j < C::VEC; ++j) x[v * C::VEC + j] = w[j];
     }
   } else {
+    // position bits of k and of the thread are disjoint, so pad(pos(tid, k)) = pad(pos(tid, 0)) + a compile-time offset:
+    // one base register per pass and immediate offsets instead of E computed addresses
+    const Word *base = tile + C::pad(pass_pos<C, PASS>(tid, 0));
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = tile[C::pad(pass_pos<C, PASS>(tid, k))];
+    for (int k = 0; k < C::E; ++k) x[k] = base[C::pad_k(k << c)];
   }
 }
 template <class C, int PASS> __device__ __forceinline__ void tile_store(const typename C::Word (&x)[C::E], typename C::Word *tile, int tid) {
@@ -220,8 +240,9 @@ template <class C, int PASS> __device__ __forceinline__ void tile_store(const ty
       row[v] = t;
     }
   } else {
+    Word *base = tile + C::pad(pass_pos<C, PASS>(tid, 0));
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) tile[C::pad(pass_pos<C, PASS>(tid, k))] = x[k];
+    for (int k = 0; k < C::E; ++k) base[C::pad_k(k << c)] = x[k];
   }
 }
 
@@ -339,6 +360,65 @@ template <class C> struct InvChain<C, C::SPLIT> {
                                              typename C::Word, typename C::Word, const typename C::TW, int, int, int) {}
 };
 
+// ---- which sub-block a unit slot works on next ------------------------------------------------------------------
+
+// Static: slot s of CTA `rank` takes sub-blocks rank*SLOTS + s, + ctas_per_residue*SLOTS, ...
+// Dynamic: the slot's first thread claims the next index of its residue with one atomicAdd, issued a whole unit ahead
+// (the returned value is only consumed at the end of the current unit, so its latency is hidden), and hands it to the
+// other threads of the slot through a double-buffered shared-memory word and the slot's barrier.
+template <class C> struct UnitWalk {
+  uint32_t *cnt;        // this residue's counter
+  uint32_t *box;        // this slot's two mailbox words (SLOTS apart)
+  uint32_t ahead, cur;  // leader only: index claimed for the next iteration; all: current index
+  uint32_t stride;
+  int par, slot, lane_base;
+  bool leader;
+  static __device__ __forceinline__ uint32_t claim(uint32_t *counter) {
+    uint32_t v;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ UnitWalk(const NttArgs &a, unsigned char *smem, int cm, int rank, int slot_, int tl, int lane_base_)
+      : cnt(a.sched + cm), box(reinterpret_cast<uint32_t *>(smem + C::TW_BYTES + 16) + slot_), ahead(0),
+        cur((uint32_t)rank * C::SLOTS + slot_), stride(a.ctas_per_residue * C::SLOTS), par(0), slot(slot_), lane_base(lane_base_),
+        leader(tl == 0) {
+    if (C::DYNAMIC) {
+      if (leader) box[0] = claim(cnt);
+      unit_sync<C>(slot, lane_base);
+      cur = box[0];
+      par = C::SLOTS;
+    }
+  }
+  __device__ __forceinline__ uint32_t index() const { return cur; }
+  // call at the top of an iteration
+  __device__ __forceinline__ void claim_ahead() {
+    if (C::DYNAMIC && !C::CLAIM_LATE && leader) ahead = claim(cnt);
+  }
+  // call at the bottom of an iteration; in dynamic mode this is also a slot-wide barrier
+  __device__ __forceinline__ void advance() {
+    if (C::DYNAMIC) {
+      if (leader) box[par] = C::CLAIM_LATE ? claim(cnt) : ahead;
+      unit_sync<C>(slot, lane_base);
+      cur = box[par];
+      par ^= C::SLOTS;
+    } else {
+      cur += stride;
+    }
+  }
+  // after the loop: the last CTA of the grid to get here re-arms the counters for the next launch
+  __device__ __forceinline__ static void finish(const NttArgs &a) {
+    if (C::DYNAMIC) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(a.sched + a.nmoduli, 1u) == gridDim.x - 1) {
+          for (uint32_t i = 0; i <= a.nmoduli; ++i) a.sched[i] = 0;
+        }
+      }
+    }
+  }
+};
+
 // ---- kernels -------------------------------------------------------------------------------------------------
 
 template <class C> __device__ __forceinline__ const typename C::TW *stage_twiddles(const NttArgs &a, int cm, unsigned char *smem) {
@@ -373,14 +453,17 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tl & 31);
-  Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
+  Word *tile = reinterpret_cast<Word *>(smem + C::TILE_OFF) + (size_t)slot * C::TILE_WORDS;
   const Store *src = reinterpret_cast<const Store *>(a.src);
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
   // one iteration = one sub-block (= one whole unit when SPLIT == 0)
-  const uint64_t nblocks = (uint64_t)a.batch << C::LOGG;
-  for (uint64_t j = (uint64_t)rank * C::SLOTS + slot; j < nblocks; j += (uint64_t)a.ctas_per_residue * C::SLOTS) {
-    const uint32_t b = (uint32_t)(j >> C::LOGG), g = (uint32_t)(j & ((1u << C::LOGG) - 1));
+  const uint32_t nblocks = a.batch << C::LOGG;  // the launcher keeps batch << LOGG below 2^31
+  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
+  for (; walk.index() < nblocks; walk.advance()) {
+    walk.claim_ahead();
+    const uint32_t j = walk.index();
+    const uint32_t b = j >> C::LOGG, g = j & ((1u << C::LOGG) - 1);
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
     const int tid = (int)(g * C::TPU) + tl;  // index inside the whole unit
     Word x[C::E];
@@ -397,7 +480,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
       }
     } else {
       const size_t bbase = ubase + (size_t)g * C::B;
-      unit_sync<C>(slot, lane_base);  // previous sub-block's copy-out has finished reading the tile
+      if (!C::DYNAMIC) unit_sync<C>(slot, lane_base);  // previous sub-block's copy-out has finished reading the tile (advance() syncs in dynamic mode)
       tile_store<C, S>(x, tile, tid);
       FwdChain<C, S + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
@@ -405,6 +488,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
       else tile_to_gmem<C>(tile, dst + bbase, tl);
     }
   }
+  UnitWalk<C>::finish(a);
 }
 
 template <int LB, int LOGN>
@@ -421,13 +505,16 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tl & 31);
-  Word *tile = reinterpret_cast<Word *>(smem + C::TW_BYTES + 16) + (size_t)slot * C::TILE_WORDS;
+  Word *tile = reinterpret_cast<Word *>(smem + C::TILE_OFF) + (size_t)slot * C::TILE_WORDS;
   const Store *src = reinterpret_cast<const Store *>(a.src);
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
-  const uint64_t nblocks = (uint64_t)a.batch << C::LOGG;
-  for (uint64_t j = (uint64_t)rank * C::SLOTS + slot; j < nblocks; j += (uint64_t)a.ctas_per_residue * C::SLOTS) {
-    const uint32_t b = (uint32_t)(j >> C::LOGG), g = (uint32_t)(j & ((1u << C::LOGG) - 1));
+  const uint32_t nblocks = a.batch << C::LOGG;  // the launcher keeps batch << LOGG below 2^31
+  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
+  for (; walk.index() < nblocks; walk.advance()) {
+    walk.claim_ahead();
+    const uint32_t j = walk.index();
+    const uint32_t b = j >> C::LOGG, g = j & ((1u << C::LOGG) - 1);
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
     const int tid = (int)(g * C::TPU) + tl;
     Word x[C::E];
@@ -435,7 +522,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #pragma unroll
       for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, S>(tid, k));
     } else {
-      unit_sync<C>(slot, lane_base);  // previous sub-block's last pass has finished reading the tile
+      if (!C::DYNAMIC) unit_sync<C>(slot, lane_base);  // previous sub-block's last pass has finished reading the tile (advance() syncs in dynamic mode)
       gmem_to_tile<C>(tile, src + ubase + (size_t)g * C::B, tl);
       InvChain<C, C::NP - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
@@ -446,6 +533,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #pragma unroll
     for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, S>(tid, k)] = (Store)x[k];
   }
+  UnitWalk<C>::finish(a);
 }
 
 // Global-memory pass PASS (< SPLIT) of a split transform: every thread owns the E coefficients of one butterfly

@@ -43,6 +43,21 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
     blocks_per_sm[device] = occ > 0 ? occ : 1;
   }
   if (l.batch == 0) return cudaSuccess;
+  // the kernels index sub-blocks with 32 bits: larger batches go out as several launches
+  constexpr uint32_t kMaxBatch = (1u << 30) >> C::LOGG;
+  if (l.batch > kMaxBatch) {
+    const size_t poly_bytes = (size_t)l.nmoduli * C::N * sizeof(typename C::Store);
+    for (uint32_t done = 0; done < l.batch; done += kMaxBatch) {
+      NttLaunch part = l;
+      part.batch = l.batch - done < kMaxBatch ? l.batch - done : kMaxBatch;
+      part.src = static_cast<const char *>(l.src) + (size_t)done * poly_bytes;
+      part.dst = static_cast<char *>(l.dst) + (size_t)done * poly_bytes;
+      if (l.other) part.other = static_cast<const char *>(l.other) + (size_t)done * poly_bytes;
+      cudaError_t e = launch_ntt_one<LB, LOGN, MODE>(part, device, num_sms, stream);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
   // persistent CTAs, each bound to one residue: grid = nmoduli * ctas_per_residue ~ one full wave
   const uint32_t resident = (uint32_t)num_sms * blocks_per_sm[device];
   uint32_t cpr = resident / l.nmoduli;
@@ -52,7 +67,7 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
   NttArgs a;
   a.src = l.src; a.dst = l.dst; a.tw = l.tw; a.moduli = l.moduli;
   a.nmoduli = l.nmoduli; a.batch = l.batch; a.ctas_per_residue = cpr;
-  a.other = l.other; a.consts = l.consts;
+  a.other = l.other; a.consts = l.consts; a.sched = l.sched;
   if constexpr (C::SPLIT > 0 && MODE != 1) {  // forward: global passes 0 .. SPLIT-1 (src -> dst), then the tile kernel in place
     cudaError_t e = launch_gpasses<LB, LOGN, 0, false>(a, C::SPLIT - 1, num_sms, stream);
     if (e != cudaSuccess) return e;

@@ -12,7 +12,25 @@
 
 #include <cstdio>
 #include <fstream>
+#include <sstream>
 #include <vector>
+
+// the friend proxy exactly as the reference's tests define it (tests/ntt_perfs.cpp:113-131)
+namespace nfl { namespace tests {
+template <class P> class poly_tests_proxy {
+  using value_type = typename P::value_type;
+public:
+  static inline bool ntt(value_type *x, const value_type *wtab, const value_type *winvtab, value_type const p) { return P::core::ntt(x, wtab, winvtab, p); }
+  static inline bool inv_ntt(value_type *x, const value_type *wtab, const value_type *winvtab, value_type invK, value_type const p) {
+    return P::core::inv_ntt(x, wtab, winvtab, invK, p);
+  }
+  static inline value_type *get_omegas(P &p, size_t cm) { return &p.base.omegas[cm][0]; }
+  static inline value_type *get_shoupomegas(P &p, size_t cm) { return &p.base.shoupomegas[cm][0]; }
+  static inline value_type *get_invomegas(P &p, size_t cm) { return &p.base.invomegas[cm][0]; }
+  static inline value_type *get_shoupinvomegas(P &p, size_t cm) { return &p.base.shoupinvomegas[cm][0]; }
+  static inline value_type get_invdegree(P &p, size_t cm) { return p.base.invpolyDegree[cm]; }
+};
+} }
 
 #define REQUIRE(cond) do { if (!(cond)) { std::fprintf(stderr, "FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); return 1; } } while (0)
 
@@ -109,6 +127,69 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
       pa.invntt_pow_invphi();
       REQUIRE(same(static_cast<PP const &>(pa).poly_obj(), x));
       REQUIRE(bool(pa == x) && !bool(pa != x));
+    }
+    // core::ntt / core::inv_ntt through the reference's friend proxy (tests/ntt_perfs.cpp:122-134,165-171), one residue at
+    // a time, against the batch entry points; and the reference-layout omega tables (core.hpp:564-581)
+    {
+      typedef nfl::tests::poly_tests_proxy<P> proxy;
+      nfl::cuda::batch<P> dx(&x, 1);
+      dx.core_ntt(); dx.download(&e);
+      c = x;
+      for (size_t cm = 0; cm < P::nmoduli; ++cm)
+        REQUIRE(proxy::ntt(&c(cm, 0), proxy::get_omegas(c, cm), proxy::get_shoupomegas(c, cm), P::get_modulus(cm)));  // always true, core.hpp:531
+      REQUIRE(same(c, e));
+      dx.core_inv_ntt(); dx.download(&e);
+      for (size_t cm = 0; cm < P::nmoduli; ++cm)
+        REQUIRE(proxy::inv_ntt(&c(cm, 0), proxy::get_invomegas(c, cm), proxy::get_shoupinvomegas(c, cm), proxy::get_invdegree(c, cm), P::get_modulus(cm)));
+      REQUIRE(same(c, e));
+      for (size_t cm = 0; cm < P::nmoduli; ++cm) {
+        const T p = P::get_modulus(cm);
+        const T *w = proxy::get_omegas(c, cm), *ws = proxy::get_shoupomegas(c, cm), *wi = proxy::get_invomegas(c, cm);
+        REQUIRE(w[0] == 1 && ws == w + P::degree);
+        T t = 1;                                                // omega has order exactly `degree`
+        for (size_t i = 0; i < P::degree / 2; ++i) { REQUIRE(w[i] == t); t = static_cast<T>((G(t) * w[1]) % p); }
+        REQUIRE(t == p - 1);
+        REQUIRE(static_cast<T>((G(w[1]) * wi[1]) % p) == 1);
+        REQUIRE(ws[1] == static_cast<T>((G(w[1]) << (8 * sizeof(T))) / p));
+        REQUIRE(w[P::degree / 2 + 1] == static_cast<T>((G(w[1]) * w[1]) % p));  // second level: powers of omega^2
+        REQUIRE(static_cast<T>((G(proxy::get_invdegree(c, cm)) * (P::degree % p)) % p) == 1);
+      }
+      bool refused = false;                                     // foreign tables are refused, not silently ignored
+      try { proxy::ntt(&c(0, 0), proxy::get_invomegas(c, 0), proxy::get_shoupinvomegas(c, 0), P::get_modulus(0)); } catch (std::runtime_error const &) { refused = true; }
+      REQUIRE(refused);
+    }
+    // random fills come from the device samplers (core.hpp:150-392): ranges and supports
+    {
+      P u1{nfl::uniform()}, u2{nfl::uniform()};
+      REQUIRE(!same(u1, u2) && bool(u1));
+      for (size_t cm = 0; cm < P::nmoduli; ++cm) for (size_t i = 0; i < P::degree; ++i) REQUIRE(u1(cm, i) < P::get_modulus(cm));
+      P nu{nfl::non_uniform(4, 2)};                             // 2 * (-4, 4), the same centred value in every residue
+      P zo{nfl::ZO_dist()};
+      P hw{nfl::hwt_dist(P::degree / 8)};
+      size_t weight = 0;
+      for (size_t i = 0; i < P::degree; ++i) {
+        const T p0 = P::get_modulus(0);
+        const T v = nu(0, i), z = zo(0, i), h = hw(0, i);
+        REQUIRE(v <= 6 || v >= p0 - 6); REQUIRE((v <= 6 ? v : p0 - v) % 2 == 0);
+        for (size_t cm = 1; cm < P::nmoduli; ++cm) {
+          const T pc = P::get_modulus(cm);
+          REQUIRE(v <= 6 ? nu(cm, i) == v : pc - nu(cm, i) == p0 - v);
+          REQUIRE((z == 0 && zo(cm, i) == 0) || (z == p0 + 1 && zo(cm, i) == pc + 1) || (z == p0 - 1 && zo(cm, i) == pc - 1));
+          REQUIRE((h == 0) == (hw(cm, i) == 0));
+        }
+        REQUIRE(z == 0 || z == p0 + 1 || z == p0 - 1);             // the reference stores +1 as p + 1 (core.hpp:343)
+        REQUIRE(h == 0 || h == p0 + 1 || h == p0 - 1);             // core.hpp:388
+        weight += h != 0;
+      }
+      REQUIRE(weight == P::degree / 8);
+      bool threw2 = false;
+      try { P bad{nfl::non_uniform(P::get_modulus(0))}; (void)bad; } catch (std::runtime_error const &) { threw2 = true; }
+      REQUIRE(threw2);                                          // core.hpp:201-206
+      std::ostringstream os;                                    // core.hpp:397-421
+      P one(1);
+      os << one;
+      const std::string term = sizeof(T) == 8 ? "ULL" : sizeof(T) == 4 ? "UL" : "U";
+      REQUIRE(os.str().substr(0, 3 + term.size() + 2) == "{ 1" + term + ", " && os.str().substr(os.str().size() - term.size() - 3) == "0" + term + " }");
     }
     free(tmp);
   }

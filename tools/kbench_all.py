@@ -9,7 +9,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import torch
 import nfllib_b200 as nb
+import nfllib_b200.capi as capi
 from oracle_lib import random_polys
+
+if os.environ.get("NFLGPU_LIB"):  # experiment builds (tools/variants.sh): time another libnflgpu.so
+    capi.lib_path = lambda: os.path.abspath(os.environ["NFLGPU_LIB"])
 
 CONFIGS = [("C2", 64, 1024, 4, 4096), ("C3", 64, 16384, 8, 1024), ("C4", 32, 4096, 14, 8192), ("C5", 64, 8192, 6, 2048),
            ("u64_2k", 64, 2048, 4, 2048), ("u64_4k", 64, 4096, 4, 1024), ("u32_1k", 32, 1024, 8, 8192), ("u32_32k", 32, 32768, 4, 512)]
