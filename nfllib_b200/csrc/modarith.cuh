@@ -23,12 +23,33 @@ template <> struct Arith<64> {
   // (measured, profiles/r01_integer_pipe_model.md: integer code on sm_100 costs ~2 issue cycles per IMAD / IMAD.WIDE /
   //  IADD3-class instruction and about twice that per IMAD.HI, so the four IMAD.WIDE of __umul64hi beat any formulation
   //  built on IMAD.HI.)
-  static __device__ __forceinline__ Word mulhi(Word a, Word b) { return __umul64hi(a, b); }
+  static __device__ __forceinline__ Word mulhi(Word a, Word b) {
+    return __umul64hi(a, b);
+  }
   // y*w - floor(y*ws / 2^64)*p  in [0, 2p) for any 64-bit y  (algos.hpp:37-38).  `np` is -p mod 2^64 (kept opaque
   // to the optimiser by the caller) so the whole right-hand side is one multiply-accumulate chain, no subtraction.
   static __device__ __forceinline__ Word mul_shoup_lazy(Word y, Word w, Word ws, Word np) {
     const Word q = mulhi(y, ws);
+#if !defined(NFLGPU_MAD_CHAIN) || NFLGPU_MAD_CHAIN
+    // lo64(y*w + q*np) as two IMAD.WIDE on one 64-bit accumulator and four IMAD on its high word: six instructions, no
+    // separate additions of the cross products
+    uint32_t y0 = (uint32_t)y, y1 = (uint32_t)(y >> 32), w0 = (uint32_t)w, w1 = (uint32_t)(w >> 32);
+    uint32_t q0 = (uint32_t)q, q1 = (uint32_t)(q >> 32), n0 = (uint32_t)np, n1 = (uint32_t)(np >> 32);
+    Word r;
+    asm("{\n\t.reg .b64 acc;\n\t.reg .b32 lo, hi;\n\t"
+        "mul.wide.u32 acc, %1, %3;\n\t"
+        "mad.wide.u32 acc, %5, %7, acc;\n\t"
+        "mov.b64 {lo, hi}, acc;\n\t"
+        "mad.lo.u32 hi, %2, %3, hi;\n\t"
+        "mad.lo.u32 hi, %1, %4, hi;\n\t"
+        "mad.lo.u32 hi, %6, %7, hi;\n\t"
+        "mad.lo.u32 hi, %5, %8, hi;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}"
+        : "=l"(r) : "r"(y0), "r"(y1), "r"(w0), "r"(w1), "r"(q0), "r"(q1), "r"(n0), "r"(n1));
+    return r;
+#else
     return y * w + q * np;
+#endif
   }
 };
 

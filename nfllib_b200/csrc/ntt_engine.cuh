@@ -84,7 +84,9 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr bool DYNAMIC = NFLGPU_DYNAMIC != 0;
   static constexpr bool CLAIM_LATE = NFLGPU_DYNAMIC == 2;  // claim at the bottom of the iteration (no register carried through the unit)
 #else
-  static constexpr bool DYNAMIC = true;
+  // measured on B200 (profiles/r01d_kbench_all.txt): -4 .. -11 % time for N >= 2048 and for the 32-bit N = 1024 kernels, +3 % for
+  // N = 1024 x 64-bit (its ~7 small units per slot already balance; the extra loop state costs instructions there)
+  static constexpr bool DYNAMIC = LOGN >= 11 || (LB != 64 && LOGN == 10);
   static constexpr bool CLAIM_LATE = false;
 #endif
   static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
