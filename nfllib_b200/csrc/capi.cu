@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace nflgpu {
@@ -77,11 +78,12 @@ struct nflgpu_ctx {
   int lift_words = 0;
   uint64_t *d_lift = nullptr;  // [inv | c64 | qhat (M*W) | q (W)]
   std::atomic<uint64_t> launches{0};
-  // dynamic unit scheduling of the NTT kernels: kSchedSlots independent sets of nmoduli + 1 counters, used round-robin so
-  // launches in flight on different streams never share one (each launch leaves its set zeroed again)
-  static constexpr uint64_t kSchedSlots = 256;
-  uint32_t *d_sched = nullptr;
-  std::atomic<uint64_t> sched_seq{0};
+  // dynamic unit scheduling of the NTT kernels (ntt_engine.cuh UnitWalk): one set of nmoduli + 1 device counters per
+  // stream, created the first time the stream is seen.  Launches on one stream are ordered and every launch leaves its set
+  // zeroed, so a set is never shared by two running kernels.  (A CUDA graph must be replayed on the stream it was captured
+  // from, after one eager call on that stream has created the set.)
+  std::mutex sched_mu;
+  std::unordered_map<void *, uint32_t *> sched_by_stream;
   static constexpr int kStages = 4;
   HostStage stage[kStages];
   size_t stage_polys = 0;  // capacity of every staging buffer, in polynomials
@@ -161,7 +163,15 @@ int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch,
   l.tw = raw ? (mode == 1 ? ctx->d_tw_raw_inv : ctx->d_tw_raw_fwd) : (mode == 1 ? ctx->d_tw_inv : ctx->d_tw_fwd);
   l.nmoduli = (uint32_t)ctx->nmoduli; l.batch = (uint32_t)batch;
   l.other = other; l.consts = ctx->d_consts;
-  l.sched = ctx->d_sched + (ctx->sched_seq.fetch_add(1) % nflgpu_ctx::kSchedSlots) * (ctx->nmoduli + 1);
+  {
+    std::lock_guard<std::mutex> lock(ctx->sched_mu);
+    uint32_t *&set = ctx->sched_by_stream[stream];
+    if (!set) {
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&set), (ctx->nmoduli + 1) * sizeof(uint32_t)));
+      CUDA_TRY(cudaMemset(set, 0, (ctx->nmoduli + 1) * sizeof(uint32_t)));
+    }
+    l.sched = set;
+  }
   CUDA_TRY(launch_ntt(ctx->limb_bits, ctx->log2_degree, mode, l, ctx->device, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
   return NFLGPU_OK;
@@ -305,8 +315,6 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
   CTX_TRY(cudaMemcpy(ctx->d_moduli_word, words.data(), words.size(), cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_moduli64, ctx->moduli.data(), nmoduli * 8, cudaMemcpyHostToDevice));
   CTX_TRY(cudaMemcpy(ctx->d_consts, consts.data(), nmoduli * 8, cudaMemcpyHostToDevice));
-  CTX_TRY(cudaMalloc(reinterpret_cast<void **>(&ctx->d_sched), nflgpu_ctx::kSchedSlots * (nmoduli + 1) * sizeof(uint32_t)));
-  CTX_TRY(cudaMemset(ctx->d_sched, 0, nflgpu_ctx::kSchedSlots * (nmoduli + 1) * sizeof(uint32_t)));
 #undef CTX_TRY
   *out = ctx;
   return NFLGPU_OK;
@@ -320,7 +328,8 @@ int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
     for (int i = 0; i < 4; ++i) { if (s.dev[i]) cudaFree(s.dev[i]); if (s.pin[i]) cudaFreeHost(s.pin[i]); }
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts); cudaFree(ctx->d_sched);
+  cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
+  for (auto &kv : ctx->sched_by_stream) cudaFree(kv.second);
   delete ctx;
   return NFLGPU_OK;
 }

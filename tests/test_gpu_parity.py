@@ -400,6 +400,38 @@ def test_hwt_sampler():
         assert np.array_equal(got, ref)
 
 
+def test_unit_scheduler_rearms_across_many_launches_and_streams():
+    """The NTT kernels of the larger degrees hand out (polynomial, residue) units through per-launch atomic counters that the
+    last CTA re-arms (ntt_engine.cuh UnitWalk).  Hundreds of back-to-back launches (more than the context's counter sets),
+    launches interleaved on two streams, and batches smaller / ragged against the grid must all stay bit-exact."""
+    import torch
+    for bits, N, M in ((64, 2048, 3), (32, 4096, 2), (64, 32768, 1)):
+        c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+        for batch in (1, 3, 37):
+            a = random_polys(bits, N, M, batch, 1000 + batch)
+            want = o.run("fwd", a)
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            src = c.alloc(batch)
+            outs = [c.alloc(batch) for _ in range(4)]
+            c.upload(src, a, batch)
+            c.sync()
+            for i in range(300):  # > nflgpu_ctx::kSchedSlots launches in total, alternating streams and directions
+                st = (s1 if i % 2 == 0 else s2).cuda_stream
+                c.ntt_fwd(outs[i % 2], src, batch, st)
+                c.ntt_inv(outs[2 + i % 2], outs[i % 2], batch, st)
+            torch.cuda.synchronize()
+            for k in range(2):
+                got = np.empty_like(a)
+                c.download(got, outs[k], batch)
+                c.sync()
+                assert np.array_equal(got, want), (bits, N, batch, k)
+                c.download(got, outs[2 + k], batch)
+                c.sync()
+                assert np.array_equal(got, a), (bits, N, batch, k)
+            for p_ in [src] + outs:
+                c.free(p_)
+
+
 def test_graft_entry_smoke():
     """The driver's smoke() entry point itself."""
     import __graft_entry__

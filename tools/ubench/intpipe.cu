@@ -10,9 +10,10 @@ typedef uint32_t u32; typedef uint64_t u64;
 constexpr int ILP = 8;
 
 template <int MODE> __global__ void __launch_bounds__(256, 4) k(u64 *out, const u32 *seed, int iters) {
-  u64 acc[ILP]; u32 a[ILP], b[ILP], c[ILP], d[ILP];
+  u64 acc[ILP]; u32 a[ILP], b[ILP], c[ILP], d[ILP]; float f[ILP], g[ILP];
+  const u32 predsrc = seed[threadIdx.x & 255] & 1;
 #pragma unroll
-  for (int i = 0; i < ILP; ++i) { acc[i] = seed[(threadIdx.x + i) & 255]; a[i] = seed[(threadIdx.x * 7 + i) & 255] | 1; b[i] = seed[(threadIdx.x * 3 + i) & 255] | 3; c[i] = seed[(threadIdx.x * 5 + i) & 255]; d[i] = seed[(threadIdx.x * 11 + i) & 255]; }
+  for (int i = 0; i < ILP; ++i) { acc[i] = seed[(threadIdx.x + i) & 255]; a[i] = seed[(threadIdx.x * 7 + i) & 255] | 1; b[i] = seed[(threadIdx.x * 3 + i) & 255] | 3; c[i] = seed[(threadIdx.x * 5 + i) & 255]; d[i] = seed[(threadIdx.x * 11 + i) & 255]; f[i] = (float)(a[i] & 1023) * 1e-3f; g[i] = 1.0f + (float)(b[i] & 7) * 1e-6f; }
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -48,6 +49,21 @@ template <int MODE> __global__ void __launch_bounds__(256, 4) k(u64 *out, const 
           asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(a[(i + 1) % ILP]));
           asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(c[i]) : "r"(d[i]), "r"(c[(i + 1) % ILP]));
           asm volatile("{.reg .u32 t; add.u32 t, %0, %1; add.u32 %0, t, %2;}" : "+r"(d[i]) : "r"(c[i]), "r"(d[(i + 1) % ILP]));
+        } else if (MODE == 14) {  // IMAD + FFMA: fmaheavy vs fmalite
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(a[(i + 1) % ILP]));
+          asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(g[i]), "f"(f[(i + 1) % ILP]));
+        } else if (MODE == 15) {  // FFMA alone
+          asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(g[i]), "f"(f[(i + 1) % ILP]));
+        } else if (MODE == 17) {  // two IMAD (same pipe) : additive by construction
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(a[(i + 1) % ILP]));
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(c[i]) : "r"(d[i]), "r"(c[(i + 1) % ILP]));
+        } else if (MODE == 18) {  // WIDE (accumulate) + two two-source adds (a 64-bit add)
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((u32)acc[(i + 1) % ILP]), "r"(b[i]));
+          asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(c[i]) : "r"(d[i]));
+          asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(d[i]));
+        } else if (MODE == 19) {  // IMAD + SEL (predicate from a loop-invariant compare)
+          asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b[i]), "r"(a[(i + 1) % ILP]));
+          asm volatile("{.reg .pred p; setp.ne.u32 p, %2, 0; selp.u32 %0, %0, %1, p;}" : "+r"(c[i]) : "r"(d[i]), "r"(predsrc));
         } else if (MODE == 6) {  // multiply mix + the butterfly's ALU share (13 ALU-class instructions per 10 multiplies)
           asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((u32)acc[i]), "r"(b[i]));
           asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i]) : "r"((u32)(acc[i] >> 32)), "r"(a[i]));
@@ -66,7 +82,7 @@ template <int MODE> __global__ void __launch_bounds__(256, 4) k(u64 *out, const 
   }
   u64 s = 0;
 #pragma unroll
-  for (int i = 0; i < ILP; ++i) s += acc[i] + a[i] + b[i] + c[i] + d[i];
+  for (int i = 0; i < ILP; ++i) s += acc[i] + a[i] + b[i] + c[i] + d[i] + (u64)f[i] + (u64)g[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -98,6 +114,11 @@ int main() {
   run<8>("1 IMAD + 1 IADD3, disjoint registers (group; 2.0 if the pipes overlap, 4.0 if not)", out, seed);
   run<9>("1 IMAD + 1 IADD (register + immediate) (group)", out, seed);
   run<10>("1 IMAD + 2 IADD3 (group; 4.0 if overlapped, 6.0 if additive)", out, seed);
+  run<17>("2 IMAD (group; same pipe: 4.0)", out, seed);
+  run<19>("1 IMAD + 1 ISETP + 1 SEL (group)", out, seed);
+  run<15>("FFMA (group = 1 FFMA)", out, seed);
+  run<14>("1 IMAD + 1 FFMA (group; fmaheavy + fmalite)", out, seed);
+  run<18>("1 WIDE (accumulate) + 64-bit add as 2 two-source adds (group)", out, seed);
   printf("%s (cycles assume 1.965 GHz; 8 warps per sub-partition, ILP %d)\n", cudaGetErrorString(cudaDeviceSynchronize()), ILP);
   return 0;
 }
