@@ -52,6 +52,16 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int N = 1 << n;
   static constexpr int e = plan_e(n, WB);
   static constexpr int E = 1 << e;
+  // Forward butterflies of the 16-coefficient 64-bit kernels use the "top-bit" lazy range (modarith.cuh csub_top): values
+  // anywhere in [0, 2^64), conditional subtract in four instructions instead of five.  Measured on B200
+  // (gpurun_out/variants.log, round 1e): N = 1024: 126.8 -> 124.1 us per launch; the 32-coefficient kernels (4 warps per
+  // sub-partition) lose 10-13 % with it -- ptxas routes every predicated carry through one predicate register, which
+  // serialises the sixteen conditional subtracts of a stage -- so they keep the [0, 4p) form.
+#if defined(NFLGPU_LAZY64)
+  static constexpr bool TOP = NFLGPU_LAZY64 != 0 && WB == 64;
+#else
+  static constexpr bool TOP = WB == 64 && e <= 4;
+#endif
   static constexpr int NP = plan_npass(n, WB);
   static constexpr int SPLIT = plan_split(n, WB);        // leading passes run as global-memory kernels (0 unless N is huge)
   static constexpr int LOGB = plan_hi(n, WB, SPLIT);     // the tile kernel transforms sub-blocks of B = 2^LOGB words
@@ -93,7 +103,7 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
   // tile address of a position (only its offset inside the sub-block matters)
-  static __device__ __forceinline__ int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
+  static NFLGPU_DEVFN int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
   // the same for a compile-time position offset made of register-index bits only (below B by construction)
   static __host__ __device__ constexpr int pad_k(int off) { return off + (off >> e) * PADW; }
 };
@@ -142,13 +152,23 @@ template <class C> __device__ __forceinline__ void unit_sync(int slot, int lane_
 
 // ---- butterfly networks on the register window -------------------------------------------------------------
 
-// Forward pass PASS: stages s0 .. s0+r-1, Cooley-Tukey, values lazily kept in [0, 4p).
+// position (inside the unit) of register k of thread `tid` in pass PASS; `tid` is the thread's index inside the whole
+// unit: for split transforms (sub-block number << log2(TPU)) | index inside the sub-block
+template <class C, int PASS> NFLGPU_DEVFN int pass_pos(int tid, int k) {
+  constexpr int hi = plan_hi(C::n, C::WB, PASS), c = plan_c(C::n, C::WB, PASS);
+  const int g = tid >> c, l = tid & ((1 << c) - 1);
+  return (g << hi) | (k << c) | l;
+}
+
+// Forward pass PASS: stages s0 .. s0+r-1, Cooley-Tukey, values lazily kept in [0, 4p) (32-bit words) or anywhere in
+// [0, 2^64) (64-bit words, C::TOP).
 // tw points at this pass's entry [0][g]; consecutive e_idx are G entries apart.
-template <class C, int PASS> __device__ __forceinline__ void fwd_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
+template <class C, int PASS> NFLGPU_DEVFN void fwd_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
                                                                       typename C::Word np, typename C::Word twop) {
   typedef typename C::A A;
   typedef typename C::Word Word;
   constexpr int r = plan_r(C::n, C::WB, PASS), G = 1 << plan_s0(C::n, C::WB, PASS), e = C::e;
+  const Word n2p = np + np;  // -2p
 #pragma unroll
   for (int q = 0; q < r; ++q) {
     const int bit = e - 1 - q;
@@ -158,19 +178,21 @@ template <class C, int PASS> __device__ __forceinline__ void fwd_pass(typename C
       const int eidx = (1 << q) - 1 + (k >> (e - q));
       const typename C::TW t = tw[eidx * G];
       Word X = x[k];
-      if (!(PASS == 0 && q == 0)) X = csub_lazy(X, twop);  // first stage sees canonical input
+      if (!(PASS == 0 && q == 0)) X = C::TOP ? csub_top(X, n2p) : csub_lazy(X, twop);  // first stage sees canonical input
       const Word T = A::mul_shoup_lazy(x[k | (1 << bit)], A::tw_w(t), A::tw_ws(t), np);
       x[k] = X + T;
-      x[k | (1 << bit)] = X - T + twop;
+      x[k | (1 << bit)] = C::TOP ? subadd(X, T, twop) : X - T + twop;
     }
   }
 }
 
 // Inverse pass PASS: stages s0+r-1 .. s0 (reverse order), Gentleman-Sande, values lazily kept in [0, 2p);
 // the very last stage (PASS 0, q 0) also multiplies by N^-1 and produces canonical values.
-template <class C, int PASS> __device__ __forceinline__ void inv_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
-                                                                      typename C::Word p, typename C::Word np, typename C::Word twop,
-                                                                      const typename C::TW ninv) {
+// (A top-bit variant of this direction -- sums held with the bias 2^63 - 2p so that "U + V >= 2p" is a sign bit -- was built
+// and measured on B200: same instruction count gain as the forward one, no time gain at any size; not kept.)
+template <class C, int PASS> NFLGPU_DEVFN void inv_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
+                                                       typename C::Word p, typename C::Word np, typename C::Word twop,
+                                                       const typename C::TW ninv) {
   typedef typename C::A A;
   typedef typename C::Word Word;
   constexpr int r = plan_r(C::n, C::WB, PASS), G = 1 << plan_s0(C::n, C::WB, PASS), e = C::e;
@@ -195,14 +217,13 @@ template <class C, int PASS> __device__ __forceinline__ void inv_pass(typename C
   }
 }
 
-// position (inside the unit) of register k of thread `tid` in pass PASS; `tid` is the thread's index inside the whole
-// unit: for split transforms (sub-block number << log2(TPU)) | index inside the sub-block
-template <class C, int PASS> __device__ __forceinline__ int pass_pos(int tid, int k) {
-  constexpr int hi = plan_hi(C::n, C::WB, PASS), c = plan_c(C::n, C::WB, PASS);
-  const int g = tid >> c, l = tid & ((1 << c) - 1);
-  return (g << hi) | (k << c) | l;
+// lazy forward value -> canonical (core.hpp:523-529)
+template <class C> NFLGPU_DEVFN typename C::Word fwd_canon(typename C::Word v, typename C::Word p, typename C::Word twop) {
+  if (C::TOP) return canon_full(v, p, ((typename C::Word)1 << (C::WB - 2)) - p);
+  return csub_lazy(csub_lazy(v, twop), p);
 }
-template <class C, int PASS> __device__ __forceinline__ const typename C::TW *pass_tw(const typename C::TW *tw, int tid) {
+
+template <class C, int PASS> NFLGPU_DEVFN const typename C::TW *pass_tw(const typename C::TW *tw, int tid) {
   constexpr int c = plan_c(C::n, C::WB, PASS), off = plan_off(C::n, C::WB, PASS);
   return tw + off + (tid >> c);
 }
@@ -334,7 +355,7 @@ template <class C, int PASS> struct FwdChain {
     fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
     if (PASS == C::NP - 1) {
 #pragma unroll
-      for (int k = 0; k < C::E; ++k) x[k] = csub_lazy(csub_lazy(x[k], twop), p);  // [0,4p) -> canonical (core.hpp:523-529)
+      for (int k = 0; k < C::E; ++k) x[k] = fwd_canon<C>(x[k], p, twop);
     }
     tile_store<C, PASS>(x, tile, tid);
     FwdChain<C, PASS + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
@@ -476,7 +497,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     if (C::NP - S == 1) {
 #pragma unroll
       for (int k = 0; k < C::E; ++k) {
-        Word v = csub_lazy(csub_lazy(x[k], twop), p);
+        Word v = fwd_canon<C>(x[k], p, twop);
         if (MUL) v = PW<LB>::mulmod(v, (Word)__ldg(reinterpret_cast<const Store *>(a.other) + ubase + pass_pos<C, S>(tid, k)), p, a.consts[cm]);
         dst[ubase + pass_pos<C, S>(tid, k)] = (Store)v;
       }

@@ -1,0 +1,101 @@
+// TEST INFRASTRUCTURE (CPU, no GPU needed): runs the butterfly networks of the NTT kernels on the host.
+//
+// nfllib_b200/csrc/ntt_engine.cuh marks fwd_pass / inv_pass / pass_pos / pass_tw / fwd_canon and the arithmetic of
+// modarith.cuh __host__ __device__; this file executes exactly those functions, pass by pass and "thread" by "thread",
+// over a plain array that stands in for the shared-memory tile / HBM slab, with the twiddle tables the product builds
+// (tables.cpp).  What it checks, on the CPU suite, is everything of the kernels that is arithmetic or index algebra:
+// the pass plan, the lazy ranges (including the 64-bit "top-bit" forward scheme), the table layout and
+// the canonicalisation.  What it cannot check — launch geometry, tile padding, barriers, TMA — is covered by the GPU suite.
+// Results are compared with the oracle by tests/test_engine_sim.py.
+#include "../../nfllib_b200/csrc/host_common.hpp"
+#include "../../nfllib_b200/csrc/ntt_engine.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace nflgpu;
+
+namespace {
+
+template <class C, int PASS> struct SimFwd {
+  static void run(typename C::Word *d, const typename C::TW *tw, typename C::Word p) {
+    typedef typename C::Word Word;
+    const Word np = opaque_neg(p), twop = 2 * p;
+    for (int tid = 0; tid < (C::N >> C::e); ++tid) {
+      Word x[C::E];
+      for (int k = 0; k < C::E; ++k) x[k] = d[pass_pos<C, PASS>(tid, k)];
+      fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
+      if (PASS == C::NP - 1)
+        for (int k = 0; k < C::E; ++k) x[k] = fwd_canon<C>(x[k], p, twop);
+      for (int k = 0; k < C::E; ++k) d[pass_pos<C, PASS>(tid, k)] = x[k];
+    }
+    SimFwd<C, PASS + 1>::run(d, tw, p);
+  }
+};
+template <class C> struct SimFwd<C, C::NP> {
+  static void run(typename C::Word *, const typename C::TW *, typename C::Word) {}
+};
+
+template <class C, int PASS> struct SimInv {
+  static void run(typename C::Word *d, const typename C::TW *tw, typename C::Word p) {
+    typedef typename C::Word Word;
+    const Word np = opaque_neg(p), twop = 2 * p;
+    const typename C::TW ninv = tw[C::N - 1];
+    for (int tid = 0; tid < (C::N >> C::e); ++tid) {
+      Word x[C::E];
+      for (int k = 0; k < C::E; ++k) x[k] = d[pass_pos<C, PASS>(tid, k)];
+      inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, np, twop, ninv);
+      for (int k = 0; k < C::E; ++k) d[pass_pos<C, PASS>(tid, k)] = x[k];
+    }
+    SimInv<C, PASS - 1>::run(d, tw, p);
+  }
+};
+template <class C> struct SimInv<C, -1> {
+  static void run(typename C::Word *, const typename C::TW *, typename C::Word) {}
+};
+
+template <int LB, int LOGN> int sim_one(int inverse, uint64_t p, uint64_t root, uint64_t kmax, uint64_t *data) {
+  typedef NttCfg<LB, LOGN> C;
+  typedef typename C::Word Word;
+  typedef typename C::TW TW;
+  ResidueTables t;
+  build_residue_tables(LB, C::WB, C::N, p, root, kmax, &t, false);
+  std::vector<TW> tw(C::N);
+  for (int i = 0; i < C::N; ++i) {
+    tw[i].x = (Word)(inverse ? t.inv_w[i] : t.fwd_w[i]);
+    tw[i].y = (Word)(inverse ? t.inv_ws[i] : t.fwd_ws[i]);
+  }
+  std::vector<Word> d(C::N);
+  for (int i = 0; i < C::N; ++i) d[i] = (Word)data[i];
+  if (inverse) SimInv<C, C::NP - 1>::run(d.data(), tw.data(), (Word)p);
+  else SimFwd<C, 0>::run(d.data(), tw.data(), (Word)p);
+  for (int i = 0; i < C::N; ++i) data[i] = (uint64_t)d[i];
+  return 0;
+}
+
+}  // namespace
+
+#define SIM_CASE(LB, LOGN) \
+  case LOGN: return sim_one<LB, LOGN>(inverse, p, root, kmax, data);
+
+// data: N residues of one (polynomial, modulus) unit, widened to uint64_t, transformed in place.
+// Returns 0, or -1 for a size this simulation is not instantiated for.
+extern "C" int nflsim_ntt(int limb_bits, int log2_degree, int inverse, uint64_t p, uint64_t root, uint64_t kmax, uint64_t *data) {
+  if (limb_bits == 64) {
+    switch (log2_degree) {
+      SIM_CASE(64, 2) SIM_CASE(64, 3) SIM_CASE(64, 4) SIM_CASE(64, 5) SIM_CASE(64, 6) SIM_CASE(64, 7) SIM_CASE(64, 8)
+      SIM_CASE(64, 9) SIM_CASE(64, 10) SIM_CASE(64, 11) SIM_CASE(64, 12) SIM_CASE(64, 13) SIM_CASE(64, 14) SIM_CASE(64, 15)
+      SIM_CASE(64, 16) SIM_CASE(64, 17)
+    }
+  } else if (limb_bits == 32) {
+    switch (log2_degree) {
+      SIM_CASE(32, 3) SIM_CASE(32, 4) SIM_CASE(32, 5) SIM_CASE(32, 6) SIM_CASE(32, 7) SIM_CASE(32, 8) SIM_CASE(32, 9)
+      SIM_CASE(32, 10) SIM_CASE(32, 11) SIM_CASE(32, 12) SIM_CASE(32, 13) SIM_CASE(32, 14) SIM_CASE(32, 15)
+    }
+  } else if (limb_bits == 16) {
+    switch (log2_degree) {
+      SIM_CASE(16, 4) SIM_CASE(16, 5) SIM_CASE(16, 6) SIM_CASE(16, 7) SIM_CASE(16, 8) SIM_CASE(16, 9)
+    }
+  }
+  return -1;
+}

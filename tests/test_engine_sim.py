@@ -1,0 +1,69 @@
+"""CPU check of the kernels' own butterfly code: tests/cpp/engine_sim.cu runs ntt_engine.cuh's fwd_pass / inv_pass /
+pass_pos / pass_tw / fwd_canon (compiled for the host) pass by pass over one unit, with the twiddle tables the product builds,
+and the result must equal the oracle's ntt_pow_phi / invntt_pow_invphi bit for bit — for every limb type and every size up to
+the first split transforms, on random and on edge inputs (0, p-1, deltas, alternating extremes)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle_lib import Oracle, random_polys, golden_params, DTYPES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM_SO = os.path.join(ROOT, "tests", "cpp", "libenginesim.so")
+
+_lib = None
+
+
+def sim():
+    global _lib
+    if _lib is None:
+        assert os.path.exists(SIM_SO), "run __graft_entry__.build()"
+        _lib = ctypes.CDLL(SIM_SO)
+        _lib.nflsim_ntt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                    ctypes.c_void_p]
+    return _lib
+
+
+def run_sim(bits, N, M, polys, inverse):
+    g = golden_params(bits)
+    out = np.empty_like(polys)
+    n = N.bit_length() - 1
+    for b in range(polys.shape[0]):
+        for cm in range(M):
+            d = np.ascontiguousarray(polys[b, cm].astype(np.uint64))
+            rc = sim().nflsim_ntt(bits, n, int(inverse), g["P"][cm], g["roots"][cm], g["kmax"], d.ctypes.data)
+            assert rc == 0, (bits, N)
+            out[b, cm] = d.astype(DTYPES[bits])
+    return out
+
+
+def edge_polys(bits, N, M):
+    g = golden_params(bits)
+    P = np.array(g["P"][:M], dtype=np.uint64)
+    e = np.zeros((6, M, N), dtype=DTYPES[bits])
+    e[1] = (P - 1)[:, None].astype(DTYPES[bits])           # all p-1
+    e[2, :, 0] = 1                                           # delta_0
+    e[3, :, 1 % N] = 1                                       # X
+    e[4, :, N - 1] = (P - 1).astype(DTYPES[bits])            # -X^(N-1)
+    e[5, :, ::2] = (P - 1)[:, None].astype(DTYPES[bits])    # alternating p-1, 0
+    return e
+
+
+SIZES = ([(64, 1 << n) for n in range(2, 18)] + [(32, 1 << n) for n in range(3, 16)] + [(16, 1 << n) for n in range(4, 10)])
+
+
+@pytest.mark.parametrize("bits,N", SIZES)
+def test_kernel_butterfly_networks_on_the_host_match_the_oracle(bits, N):
+    M = 2
+    o = Oracle(bits, N, M)
+    count = 3 if N <= 4096 else 1
+    a = np.concatenate([random_polys(bits, N, M, count, 7000 + N), edge_polys(bits, N, M)])
+    want = o.run("fwd", a)
+    got = run_sim(bits, N, M, a, inverse=False)
+    assert np.array_equal(got, want)
+    back = run_sim(bits, N, M, want, inverse=True)
+    assert np.array_equal(back, a)
+    # the inverse on arbitrary canonical input (not only on forward outputs)
+    assert np.array_equal(run_sim(bits, N, M, a, inverse=True), o.run("inv", a))

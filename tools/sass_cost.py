@@ -21,21 +21,21 @@ def kernels(path, hot_loop=True):
             cur = m.group(1)
             body[cur] = []
             continue
-        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)\s*([^;]*);", line)
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(@!?U?P\w+\s+)?([A-Z0-9_.]+)\s*([^;]*);", line)
         if m and cur:
-            body[cur].append((int(m.group(1), 16), m.group(2), m.group(3)))
+            body[cur].append((int(m.group(1), 16), m.group(3), m.group(4), bool(m.group(2))))
     res = {}
     for name, ins in body.items():
         lo, hi = 0, 1 << 60
         if hot_loop:
             best = 0
-            for addr, op, args in ins:
-                if op.startswith("BRA"):
+            for addr, op, args, pred in ins:
+                if op.startswith("BRA") and pred:  # the unit loop closes with a predicated backward branch (an unpredicated one is the mbarrier wait)
                     t = re.search(r"0x([0-9a-f]+)\s*$", args.strip())
                     if t and int(t.group(1), 16) < addr and addr - int(t.group(1), 16) > best:
                         best = addr - int(t.group(1), 16)
                         lo, hi = int(t.group(1), 16), addr
-        res[name] = [op for addr, op, _ in ins if lo <= addr <= hi]
+        res[name] = [op for addr, op, _, _ in ins if lo <= addr <= hi]
     return res
 
 
