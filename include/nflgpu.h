@@ -164,6 +164,43 @@ int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8
  * sequence (an index rejection exactly at a refill boundary, probability < 2^-44 per draw, would shift the reference's). */
 int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce, void *stream);
 
+/* poly::set(nfl::gaussian<in_class, T, lu_depth>(&prng, amplifier)) (core.hpp:284-325, poly.hpp:61-67) over
+ * nfl::FastGaussianNoise<in_class, T, lu_depth>(sigma, security, samples, center) (prng/FastGaussianNoise.hpp).
+ *
+ * nflgpu_gaussian_create builds what the reference's constructor builds — tail bound, precision, the cumulative
+ * distribution ("barrier") table in MPFR arithmetic, the look-up tables (FastGaussianNoise.hpp:233-476) — bit-identical to
+ * the reference's: the table is computed with the same MPFR calls, through the MPFR/GMP runtimes (libmpfr.so.6,
+ * libgmp.so.10) opened on first use; without them it returns NFLGPU_ERR_UNSUPPORTED (MPFR is a build dependency of the
+ * reference itself).  nflgpu_gaussian_create_from_barriers takes a barrier table computed elsewhere instead:
+ * nbarriers rows of word_precision look-up words of in_bytes bytes, most significant word first, as the reference holds them.
+ *   in_bytes 1 | 2 = in_class uint8_t | uint16_t;  lu_depth 1 | 2;  supported shapes: (1, 1), (1, 2), (2, 1).
+ * A sampler belongs to the context's device and can be used with any context on that device.
+ *
+ * nflgpu_gaussian_sample writes `batch` successive draws into a device batch, the reference's PRNG being at nonce
+ * first_nonce before the first one.  getNoise() refills its keystream buffer a data-dependent number of times
+ * (FastGaussianNoise.hpp:601-610), so the nonce a draw starts with depends on all draws before it; the device evaluates every
+ * possible starting nonce of a window in parallel and then follows the chain (csrc/sampler.cu), which reproduces the
+ * sequential reference bit for bit.  *nonces_used (optional) receives the number of fastrandombytes calls the batch made, i.e.
+ * where the stream continues.  The call synchronises `stream` before returning. */
+typedef struct nflgpu_gaussian nflgpu_gaussian;
+int nflgpu_gaussian_create(nflgpu_gaussian **g, nflgpu_ctx *ctx, double sigma, unsigned security, unsigned samples, double center,
+                           int in_bytes, int lu_depth);
+int nflgpu_gaussian_create_from_barriers(nflgpu_gaussian **g, nflgpu_ctx *ctx, const void *barriers, size_t nbarriers,
+                                         size_t word_precision, int in_bytes, int lu_depth, int64_t rounded_center);
+int nflgpu_gaussian_destroy(nflgpu_gaussian *g);
+/* The host part alone (no device needed): the parameters and the barrier table nflgpu_gaussian_create would build.
+ * info as in nflgpu_gaussian_info (the flag counters are those of lu_depth); `barriers` may be NULL to query the size
+ * (info[0] * info[1] * in_bytes bytes), otherwise `capacity` bytes must hold it. */
+int nflgpu_gaussian_table(double sigma, unsigned security, unsigned samples, double center, int in_bytes, int lu_depth,
+                          int64_t info[7], double *tail_bound, void *barriers, size_t capacity);
+/* info[0..6] = number of barriers, word precision, bit precision, flagged first-level entries, flagged second-level entries,
+ * rounded center, look-up table size — the private members of the reference object, for parity checks */
+int nflgpu_gaussian_info(const nflgpu_gaussian *g, int64_t info[7], double *tail_bound);
+/* copies the barrier table: info[0] * info[1] * in_bytes bytes */
+int nflgpu_gaussian_barriers(const nflgpu_gaussian *g, void *out);
+int nflgpu_gaussian_sample(nflgpu_ctx *ctx, const nflgpu_gaussian *g, void *dst, size_t batch, uint64_t amplifier,
+                           const uint8_t key[32], uint64_t first_nonce, uint64_t *nonces_used, void *stream);
+
 /* ---- CRT lift: the consumer that needs all residues of a polynomial on one device ------------------------- */
 
 /* poly::GMP::poly2mpz / mpz2poly (include/nfl/gmp.hpp:183-219) without GMP types: a lifted coefficient is

@@ -59,6 +59,15 @@ def lib():
         L.nflgpu_non_uniform.argtypes = [vp, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_zo.argtypes = [vp, vp, sz, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_hwt.argtypes = [vp, vp, sz, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, vp]
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        L.nflgpu_gaussian_create.argtypes = [ctypes.POINTER(vp), vp, ctypes.c_double, ctypes.c_uint, ctypes.c_uint, ctypes.c_double, ci, ci]
+        L.nflgpu_gaussian_create_from_barriers.argtypes = [ctypes.POINTER(vp), vp, vp, sz, sz, ci, ci, ctypes.c_int64]
+        L.nflgpu_gaussian_destroy.argtypes = [vp]
+        L.nflgpu_gaussian_info.argtypes = [vp, i64p, ctypes.POINTER(ctypes.c_double)]
+        L.nflgpu_gaussian_barriers.argtypes = [vp, vp]
+        L.nflgpu_gaussian_table.argtypes = [ctypes.c_double, ctypes.c_uint, ctypes.c_uint, ctypes.c_double, ci, ci, i64p,
+                                            ctypes.POINTER(ctypes.c_double), vp, sz]
+        L.nflgpu_gaussian_sample.argtypes = [vp, vp, vp, sz, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, u64p, vp]
         L.nflgpu_lift_words.argtypes = [vp, ctypes.POINTER(sz)]
         L.nflgpu_poly2mpz.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_mpz2poly.argtypes = [vp, vp, vp, sz, vp]
@@ -82,6 +91,58 @@ def params(bits, first, count):
     arrs = [np.zeros(count, np.uint64) for _ in range(4)]
     _check(lib().nflgpu_params(bits, first, count, *[a.ctypes.data for a in arrs]))
     return dict(zip(("P", "Pn", "roots", "invkmax"), arrs))
+
+
+INFO_KEYS = ("nb", "wp", "bit_precision", "flag_ctr1", "flag_ctr2", "rounded_center", "lu_size")
+
+
+def gaussian_table(sigma, security, samples, center=0.0, in_bytes=1, lu_depth=2):
+    """nflgpu_gaussian_table (host only): (params dict, barriers[nb][wp]) of FastGaussianNoise<in_class, T, lu_depth>(sigma,
+    security, samples, center)."""
+    info = (ctypes.c_int64 * 7)()
+    tb = ctypes.c_double()
+    _check(lib().nflgpu_gaussian_table(sigma, security, samples, center, in_bytes, lu_depth, info, ctypes.byref(tb), None, 0))
+    bar = np.zeros((info[0], info[1]), dtype=np.uint8 if in_bytes == 1 else np.uint16)
+    _check(lib().nflgpu_gaussian_table(sigma, security, samples, center, in_bytes, lu_depth, info, ctypes.byref(tb), bar.ctypes.data, bar.nbytes))
+    d = dict(zip(INFO_KEYS, list(info)))
+    d["tail_bound"] = tb.value
+    return d, bar
+
+
+class Gaussian:
+    """nflgpu_gaussian: nfl::FastGaussianNoise<in_class, T, lu_depth> on a context's device."""
+
+    def __init__(self, ctx, sigma=None, security=128, samples=1 << 14, center=0.0, in_bytes=1, lu_depth=2, barriers=None, rounded_center=0):
+        self.ctx, self.in_bytes, self.lu_depth = ctx, in_bytes, lu_depth
+        h = ctypes.c_void_p()
+        if barriers is not None:
+            b = np.ascontiguousarray(barriers)
+            _check(lib().nflgpu_gaussian_create_from_barriers(ctypes.byref(h), ctx.h, b.ctypes.data, b.shape[0], b.shape[1], in_bytes, lu_depth,
+                                                              rounded_center))
+        else:
+            _check(lib().nflgpu_gaussian_create(ctypes.byref(h), ctx.h, sigma, security, samples, center, in_bytes, lu_depth))
+        self.h = h
+
+    def info(self):
+        info = (ctypes.c_int64 * 7)()
+        tb = ctypes.c_double()
+        _check(lib().nflgpu_gaussian_info(self.h, info, ctypes.byref(tb)))
+        d = dict(zip(INFO_KEYS, list(info)))
+        d["tail_bound"] = tb.value
+        return d
+
+    def sample(self, dst, batch, key, first_nonce, amplifier=1, stream=0):
+        """nflgpu_gaussian_sample; returns the number of nonces (fastrandombytes calls) the batch consumed."""
+        used = ctypes.c_uint64()
+        _check(lib().nflgpu_gaussian_sample(self.ctx.h, self.h, dst, batch, amplifier, bytes(key), first_nonce, ctypes.byref(used), stream))
+        return used.value
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().nflgpu_gaussian_destroy(self.h)
+            self.h = None
+
+    __del__ = close
 
 
 class Context:

@@ -2,6 +2,7 @@
 // No CPU fallback anywhere: every compute entry point ends in a kernel launch or fails.
 #include "../../include/nflgpu.h"
 #include "host_common.hpp"
+#include "gaussian.h"
 #include "lift.h"
 #include "ntt_dispatch.h"
 #include "pointwise.h"
@@ -596,6 +597,146 @@ int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uin
 int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream) {
   if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
   return run_sampler(ctx, SAMPLE_ZO, dst, batch, key, first_nonce, rho, 0, 0, ctx->degree, stream);
+}
+
+struct nflgpu_gaussian {
+  nflgpu::GaussianTable t;
+  int device = 0;
+  unsigned char *d_barriers = nullptr;
+  nflgpu::GaussLutEntry *d_lut = nullptr;
+};
+
+static int gaussian_finish(nflgpu_gaussian **out, nflgpu_ctx *ctx, nflgpu_gaussian *g, int lu_depth) {
+  if (gaussian_build_luts(&g->t, lu_depth)) { delete g; return NFLGPU_ERR_UNSUPPORTED; }
+  g->device = ctx->device;
+  DeviceGuard dg(ctx->device);
+  cudaError_t e = cudaErrorInvalidDevice;
+  if (!dg.ok || (e = cudaMalloc(reinterpret_cast<void **>(&g->d_barriers), g->t.barriers.size())) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void **>(&g->d_lut), g->t.lut.size() * sizeof(GaussLutEntry))) != cudaSuccess ||
+      (e = cudaMemcpy(g->d_barriers, g->t.barriers.data(), g->t.barriers.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemcpy(g->d_lut, g->t.lut.data(), g->t.lut.size() * sizeof(GaussLutEntry), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    set_error(std::string("Gaussian table upload: ") + cudaGetErrorName(e));
+    nflgpu_gaussian_destroy(g);
+    return NFLGPU_ERR_CUDA;
+  }
+  *out = g;
+  return NFLGPU_OK;
+}
+
+int nflgpu_gaussian_create(nflgpu_gaussian **out, nflgpu_ctx *ctx, double sigma, unsigned security, unsigned samples, double center,
+                           int in_bytes, int lu_depth) {
+  if (!out || !ctx) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  *out = nullptr;
+  nflgpu_gaussian *g = new (std::nothrow) nflgpu_gaussian;
+  if (!g) { set_error("out of memory"); return NFLGPU_ERR_ALLOC; }
+  const int rc = gaussian_compute_barriers(sigma, security, samples, center, in_bytes, &g->t);
+  if (rc) { delete g; return rc == -1 ? NFLGPU_ERR_ARG : NFLGPU_ERR_UNSUPPORTED; }
+  return gaussian_finish(out, ctx, g, lu_depth);
+}
+
+int nflgpu_gaussian_create_from_barriers(nflgpu_gaussian **out, nflgpu_ctx *ctx, const void *barriers, size_t nbarriers,
+                                         size_t word_precision, int in_bytes, int lu_depth, int64_t rounded_center) {
+  if (!out || !ctx || !barriers) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  *out = nullptr;
+  if ((in_bytes != 1 && in_bytes != 2) || nbarriers == 0 || nbarriers > 0x7fffffffu || word_precision == 0 ||
+      word_precision * in_bytes > GAUSS_MAX_ROW_BYTES) { set_error("bad Gaussian barrier table"); return NFLGPU_ERR_ARG; }
+  nflgpu_gaussian *g = new (std::nothrow) nflgpu_gaussian;
+  if (!g) { set_error("out of memory"); return NFLGPU_ERR_ALLOC; }
+  g->t.nb = (unsigned)nbarriers; g->t.wp = (unsigned)word_precision; g->t.in_bytes = in_bytes;
+  g->t.bit_precision = (unsigned)(word_precision * 8 * in_bytes); g->t.rounded_center = (long)rounded_center;
+  g->t.barriers.assign(static_cast<const unsigned char *>(barriers), static_cast<const unsigned char *>(barriers) + nbarriers * word_precision * in_bytes);
+  return gaussian_finish(out, ctx, g, lu_depth);
+}
+
+int nflgpu_gaussian_table(double sigma, unsigned security, unsigned samples, double center, int in_bytes, int lu_depth, int64_t info[7],
+                          double *tail_bound, void *barriers, size_t capacity) {
+  if (!info) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  nflgpu_gaussian g;
+  const int rc = gaussian_compute_barriers(sigma, security, samples, center, in_bytes, &g.t);
+  if (rc) return rc == -1 ? NFLGPU_ERR_ARG : NFLGPU_ERR_UNSUPPORTED;
+  if (gaussian_build_luts(&g.t, lu_depth)) return NFLGPU_ERR_UNSUPPORTED;
+  nflgpu_gaussian_info(&g, info, tail_bound);
+  if (barriers) {
+    if (capacity < g.t.barriers.size()) { set_error("barrier buffer too small"); return NFLGPU_ERR_ARG; }
+    std::memcpy(barriers, g.t.barriers.data(), g.t.barriers.size());
+  }
+  return NFLGPU_OK;
+}
+
+int nflgpu_gaussian_destroy(nflgpu_gaussian *g) {
+  if (!g) return NFLGPU_OK;
+  DeviceGuard dg(g->device);
+  cudaFree(g->d_barriers); cudaFree(g->d_lut);
+  delete g;
+  return NFLGPU_OK;
+}
+
+int nflgpu_gaussian_info(const nflgpu_gaussian *g, int64_t info[7], double *tail_bound) {
+  if (!g || !info) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  info[0] = g->t.nb; info[1] = g->t.wp; info[2] = g->t.bit_precision; info[3] = g->t.flag_ctr1; info[4] = g->t.flag_ctr2;
+  info[5] = g->t.rounded_center; info[6] = g->t.lu_size;
+  if (tail_bound) *tail_bound = g->t.tail_bound;
+  return NFLGPU_OK;
+}
+
+int nflgpu_gaussian_barriers(const nflgpu_gaussian *g, void *out) {
+  if (!g || !out) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  std::memcpy(out, g->t.barriers.data(), g->t.barriers.size());
+  return NFLGPU_OK;
+}
+
+int nflgpu_gaussian_sample(nflgpu_ctx *ctx, const nflgpu_gaussian *g, void *dst, size_t batch, uint64_t amplifier, const uint8_t key[32],
+                           uint64_t first_nonce, uint64_t *nonces_used, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst, "dst"))) return rc;
+  if (!g || !key) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  if (g->device != ctx->device) { set_error("Gaussian sampler belongs to another device"); return NFLGPU_ERR_ARG; }
+  if (batch > 0x3fffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (nonces_used) *nonces_used = 0;
+  if (batch == 0) return NFLGPU_OK;
+  const uint64_t words = gaussian_words_per_fill(g->t, ctx->degree);
+  // getNoise() needs room for one full-precision comparison in a fresh buffer (the reference would read past its buffer)
+  if (words <= 2ull * g->t.wp) { set_error("degree too small for this Gaussian sampler's refill logic"); return NFLGPU_ERR_UNSUPPORTED; }
+  DeviceGuard dg(ctx->device);
+  if (!dg.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  cudaStream_t s = (cudaStream_t)stream;
+  GaussArgs a;
+  a.dst = dst; a.moduli = ctx->d_moduli64;
+  for (int i = 0; i < 8; ++i)
+    a.key[i] = (uint32_t)key[4 * i] | ((uint32_t)key[4 * i + 1] << 8) | ((uint32_t)key[4 * i + 2] << 16) | ((uint32_t)key[4 * i + 3] << 24);
+  a.first_nonce = first_nonce; a.amplifier = amplifier;
+  a.poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
+  a.words_per_fill = words;
+  a.nmoduli = (uint32_t)ctx->nmoduli; a.log2_degree = (uint32_t)ctx->log2_degree; a.limb_bits = (uint32_t)ctx->limb_bits;
+  a.batch = (uint32_t)batch;
+  a.wp = g->t.wp; a.in_bytes = (uint32_t)g->t.in_bytes; a.depth = (uint32_t)g->t.depth; a.lu_size = g->t.lu_size;
+  a.barriers = g->d_barriers; a.lut = g->d_lut;
+  // a draw makes one call plus (usually at most) one refill: start with a window of two nonces per polynomial, widen if the
+  // chain runs out of it
+  for (uint64_t per_poly = 2; per_poly <= 64; per_poly *= 2) {
+    a.window = (uint32_t)(batch * per_poly + 16);
+    const size_t noise_bytes = (size_t)a.window * ctx->degree * sizeof(int32_t);
+    const size_t total = noise_bytes + (size_t)a.window * 4 + batch * 4 + 16;
+    unsigned char *scratch = nullptr;
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), total, s));
+    a.cand_noise = reinterpret_cast<int32_t *>(scratch);
+    a.cand_calls = reinterpret_cast<uint32_t *>(scratch + noise_bytes);
+    a.chosen = a.cand_calls + a.window;
+    a.result = reinterpret_cast<uint64_t *>(scratch + ((noise_bytes + (size_t)a.window * 4 + batch * 4 + 7) & ~(size_t)7));
+    cudaError_t e = launch_gaussian(a, s);
+    uint64_t result[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(result, a.result, sizeof(result), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFreeAsync(scratch, s);
+    CUDA_TRY(e);
+    ctx->launches += 3;
+    if (result[1] == 0) {
+      if (nonces_used) *nonces_used = result[0];
+      return NFLGPU_OK;
+    }
+  }
+  set_error("Gaussian sampler: refill chain did not fit the candidate window");
+  return NFLGPU_ERR_UNSUPPORTED;
 }
 
 int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, size_t batch, void *stream) {

@@ -11,6 +11,7 @@
 // poly::set(uniform) calls produce, so that with the same key the device batch is bit-identical to the reference's
 // draws (tests compare against the reference itself run with a fixed key).  One thread = one 64-byte Salsa20 block =
 // 8 / 16 / 32 limbs, written with four 16-byte stores; integer ALU only (add / rotate / xor).
+#include "gaussian.h"
 #include "pointwise.h"
 
 namespace nflgpu {
@@ -200,6 +201,111 @@ __global__ void __launch_bounds__(256) uniform_kernel(const SampleArgs a) {
       }
     }
   }
+}
+
+// ---- poly::set(gaussian) core.hpp:291-325 over FastGaussianNoise::getNoise (prng/FastGaussianNoise.hpp:478-613) ----------
+//
+// getNoise() is sequential inside a polynomial (every output consumes 1, 2 or word_precision look-up words of one keystream)
+// and, across polynomials, the NONCE a draw starts with depends on how many times the draws before it refilled their buffer
+// (refills are data dependent, :601-610).  Three kernels keep the batch parallel and the result bit-identical:
+//   1. gauss_candidates: thread c runs the complete draw that would start at nonce first_nonce + c, for every c of a window
+//      (about 2 x batch: a draw makes one call plus, typically, at most one refill) and records its outputs and its number
+//      of fastrandombytes calls;
+//   2. gauss_chain: one thread follows nonce -> nonce + calls(nonce) from first_nonce: the candidates the reference's
+//      sequential draws really are;
+//   3. gauss_expand: coalesced copy of the chosen candidates into the batch, amplified, negative values stored as p + v in
+//      every residue.
+struct NoiseStream {  // look-up words of the keystream (key, nonce), generated 64 bytes at a time
+  const uint32_t (&key)[8];
+  uint64_t nonce, blk;
+  uint32_t x[16];
+  uint32_t in_bytes;
+  __device__ NoiseStream(const uint32_t (&k)[8], uint32_t ib) : key(k), nonce(0), blk(~0ull), in_bytes(ib) {}
+  __device__ void reset(uint64_t n) { nonce = n; blk = ~0ull; }
+  __device__ uint32_t word(uint64_t j) {
+    const uint64_t byte = j * in_bytes, b = byte >> 6;
+    if (b != blk) { blk = b; salsa20_block(key, nonce, b, x); }
+    const uint32_t o = (uint32_t)byte & 63u, w = x[o >> 2] >> (8 * (o & 3));
+    return in_bytes == 1 ? (w & 0xffu) : (w & 0xffffu);  // 16-bit words never straddle a 32-bit word: o is even
+  }
+};
+
+__global__ void __launch_bounds__(64) gauss_candidates_kernel(const GaussArgs a) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= a.window) return;
+  const uint64_t degree = 1ull << a.log2_degree;
+  const uint32_t wp = a.wp, depth = a.depth;
+  int32_t *out = a.cand_noise + (uint64_t)c * degree;
+  NoiseStream ns(a.key, a.in_bytes);
+  uint64_t nonce = a.first_nonce + c, pos = 0, used = 0;
+  uint32_t calls = 1;
+  ns.reset(nonce++);
+  for (uint64_t k = 0; k < degree; ++k) {
+    const uint32_t in1 = ns.word(pos);
+    GaussLutEntry e = a.lut[in1];
+    const bool flagged1 = e.sub >= 0;
+    if (flagged1 && depth == 2) e = a.lut[(uint64_t)e.sub * a.lu_size + ns.word(pos + 1)];
+    int32_t output = e.val;
+    if (e.sub >= 0) {  // walk the barriers of this entry: +1 for every barrier not above the noise (cmp(), :617-628)
+      uint32_t nw[GAUSS_MAX_ROW_BYTES];
+      for (uint32_t j = 0; j < wp; ++j) nw[j] = ns.word(pos + j);
+      for (uint32_t b = e.bstart; b < e.bstart + e.bcount; ++b) {
+        const unsigned char *row = a.barriers + (uint64_t)b * wp * a.in_bytes;
+        int cmp = 0;
+        for (uint32_t j = 0; j < wp && cmp == 0; ++j) {
+          const uint32_t bw = a.in_bytes == 1 ? row[j] : (uint32_t)row[2 * j] | ((uint32_t)row[2 * j + 1] << 8);
+          cmp = bw > nw[j] ? 1 : (bw < nw[j] ? -1 : 0);
+        }
+        if (cmp == 1) break;
+        ++output;
+      }
+      pos += wp - depth; used += wp - depth;
+    }
+    if (flagged1 && depth == 2) { ++pos; ++used; }
+    ++pos; ++used;
+    out[k] = output;
+    if (used + wp >= a.words_per_fill) {  // :601-610
+      pos = 0; used = 0;
+      ns.reset(nonce++);
+      ++calls;
+    }
+  }
+  a.cand_calls[c] = calls;
+}
+
+__global__ void gauss_chain_kernel(const GaussArgs a) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint64_t at = 0;
+  uint32_t b = 0;
+  for (; b < a.batch && at < a.window; ++b) { a.chosen[b] = (uint32_t)at; at += a.cand_calls[at]; }
+  a.result[0] = at;
+  a.result[1] = b < a.batch ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256) gauss_expand_kernel(const GaussArgs a) {
+  const uint64_t degree = 1ull << a.log2_degree, total = (uint64_t)a.batch << a.log2_degree;
+  const uint64_t wrap = a.limb_bits == 64 ? ~0ull : ((1ull << a.limb_bits) - 1);
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t poly = t >> a.log2_degree, i = t & (degree - 1);
+    // rnd[i] is signed_value_type: getNoise stores the low limb_bits of the output, rnd *= amplifier wraps at the limb width
+    uint64_t v = (uint64_t)(int64_t)a.cand_noise[(uint64_t)a.chosen[poly] * degree + i] & wrap;
+    if (a.amplifier != 1) v = (v * a.amplifier) & wrap;
+    const bool neg = (v >> (a.limb_bits - 1)) & 1;
+    for (uint32_t cm = 0; cm < a.nmoduli; ++cm)
+      store_any(reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes, a.limb_bits, (uint64_t)cm * degree + i,
+                (neg ? a.moduli[cm] + v : v) & wrap);
+  }
+}
+
+cudaError_t launch_gaussian(const GaussArgs &a, cudaStream_t stream) {
+  if (a.batch == 0) return cudaSuccess;
+  gauss_candidates_kernel<<<(a.window + 63) / 64, 64, 0, stream>>>(a);
+  gauss_chain_kernel<<<1, 32, 0, stream>>>(a);
+  const uint64_t total = (uint64_t)a.batch << a.log2_degree;
+  uint64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gauss_expand_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream) {

@@ -182,6 +182,7 @@ void randombytes(unsigned char *x, unsigned long long xlen) {
 }
 }
 static unsigned long long g_uniform_calls = 0;  // mirrors the nonce counter inside fastrandombytes.cpp:17-34
+extern "C" unsigned long long *nflref_nonce_counter(void) { return &g_uniform_calls; }  // shared with ref_gaussian.cpp
 template <class P> static void sample_range(int kind, P *out, size_t batch, unsigned long long p0, unsigned long long p1) {
   for (size_t i = 0; i < batch; ++i) {
     if (kind == 0) out[i].set(nfl::uniform());                       // core.hpp:150-187

@@ -109,6 +109,21 @@ class Oracle:
         assert rc == 0
         return out, calls.value
 
+    def gaussian(self, batch, table, amplifier, key, first_nonce):
+        """`batch` successive poly::set(gaussian(&prng, amplifier)) draws for the barrier table `table` (a GaussTable);
+        returns (polys, number of fastrandombytes calls made)."""
+        out = np.empty((batch, self.M, self.N), dtype=self.dtype)
+        calls = ctypes.c_uint64()
+        L = self.lib()
+        L.nflo_gaussian.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                    ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64,
+                                    ctypes.POINTER(ctypes.c_uint64)]
+        bar = np.ascontiguousarray(table.barriers)
+        rc = L.nflo_gaussian(self.h, out.ctypes.data, batch, bar.ctypes.data, bar.shape[0], bar.shape[1], table.in_bytes, table.depth,
+                             table.rounded_center, amplifier, bytes(key), first_nonce, ctypes.byref(calls))
+        assert rc == 0, rc
+        return out, calls.value
+
     def zo(self, batch, rho, key, first_nonce):
         out = np.empty((batch, self.M, self.N), dtype=self.dtype)
         self.lib().nflo_zo(self.h, out.ctypes.data, batch, rho, bytes(key), first_nonce)
@@ -119,6 +134,13 @@ class Oracle:
         out = np.empty_like(a)
         self.lib().nflo_spec_fwd(self.h, out.ctypes.data, a.ctypes.data, a.size // (self.N * self.M))
         return out
+
+
+class GaussTable:
+    """A FastGaussianNoise barrier table: barriers[nb][wp] look-up words (uint8 / uint16) + the parameters that go with it."""
+
+    def __init__(self, barriers, in_bytes, depth, rounded_center, params=None):
+        self.barriers, self.in_bytes, self.depth, self.rounded_center, self.params = barriers, in_bytes, depth, rounded_center, params
 
 
 def have_ref():
@@ -173,6 +195,33 @@ class Ref:
 
     def uniform(self, batch):
         return self.sample("uniform", batch)
+
+    @classmethod
+    def gaussian_table(cls, sigma, security, samples, center, in_bytes, depth, bits=64):
+        """The reference's own FastGaussianNoise<in_class, T, depth>(sigma, security, samples, center): (handle, GaussTable)."""
+        L = cls.lib()
+        L.nflref_gaussian_create.argtypes = [ctypes.c_double, ctypes.c_uint, ctypes.c_uint, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        h = L.nflref_gaussian_create(sigma, security, samples, center, in_bytes, depth, bits)
+        assert h >= 0, h
+        info = (ctypes.c_longlong * 7)()
+        tb = ctypes.c_double()
+        assert L.nflref_gaussian_info(h, info, ctypes.byref(tb)) == 0
+        nb, wp = info[0], info[1]
+        bar = np.zeros((nb, wp), dtype=np.uint8 if in_bytes == 1 else np.uint16)
+        assert L.nflref_gaussian_barriers(h, bar.ctypes.data_as(ctypes.c_void_p)) == 0
+        params = {"nb": nb, "wp": wp, "bit_precision": info[2], "flag_ctr1": info[3], "flag_ctr2": info[4], "tail_bound": tb.value}
+        return h, GaussTable(bar, in_bytes, depth, info[5], params)
+
+    def gaussian(self, handle, batch, amplifier=1):
+        """(first_nonce, nonces_used, polys): `batch` successive poly::set(gaussian(&prng, amplifier)) of the reference, fixed key."""
+        out = aligned((batch, self.M, self.N), self.dtype)
+        first, used = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        L = self.lib()
+        L.nflref_gaussian_sample.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_ulonglong,
+                                             ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+        rc = L.nflref_gaussian_sample(handle, self.N, self.M, out.ctypes.data, batch, amplifier, ctypes.byref(first), ctypes.byref(used))
+        assert rc == 0, rc
+        return first.value, used.value, out
 
     def lift(self, polys, W):
         """The reference's own poly2mpz (GMP runtime of the image): uint64[batch][N][W]."""
