@@ -14,7 +14,7 @@
 // A single host-resident poly per call is PCIe-bound (hard part 5); throughput code should
 // use nfl::cuda::batch<poly> below, which keeps `count` polys resident in HBM between operations.
 //
-// Out of scope here: samplers other than a test-grade uniform(), GMP lifting, poly_p,
+// Out of scope here: FastGaussianNoise::getNoise for free-standing arrays, GMP lifting, poly_p,
 // serialization (the byte layout is identical, so reference-serialized polys can be memcpy'd in).
 #ifndef NFL_B200_HPP
 #define NFL_B200_HPP
@@ -136,6 +136,37 @@ struct hwt_dist {  // hamming weight distribution
 struct ZO_dist {  // P(1) = P(-1) = (rho/0xFF)/2, P(0) = 1 - P(1) - P(-1)
   uint8_t rho;
   ZO_dist(uint8_t rho_ = 0x7F) : rho(rho_) {}
+};
+
+/* Discrete Gaussian (poly.hpp:61-67, prng/FastGaussianNoise.hpp).  The object holds what the reference's constructor builds
+ * (barrier table in MPFR arithmetic, look-up tables), built by libnflgpu on first use on the device of the polynomial type that
+ * draws from it; poly::set(gaussian) / batch::set_gaussian run the look-up sampler on the device (nflgpu_gaussian_sample),
+ * bit-identical to the reference's draws under the same key and nonce.  Shapes: (uint8_t, 1 | 2), (uint16_t, 1).
+ * Not mirrored: getNoise() into a free-standing array (only polynomials are drawn), verbose output. */
+template <class in_class, class out_class, unsigned _lu_depth> class FastGaussianNoise {
+  static_assert((sizeof(in_class) == 1 && (_lu_depth == 1 || _lu_depth == 2)) || (sizeof(in_class) == 2 && _lu_depth == 1),
+                "FastGaussianNoise: in_class must be uint8_t (depth 1 or 2) or uint16_t (depth 1)");
+  double sigma_, center_;
+  unsigned security_, samples_;
+  nflgpu_gaussian *g_;
+  FastGaussianNoise(FastGaussianNoise const &);
+  FastGaussianNoise &operator=(FastGaussianNoise const &);
+
+public:
+  FastGaussianNoise(double sigma, unsigned int security, unsigned int samples, double center_d = 0, bool /*verbose*/ = false)
+      : sigma_(sigma), center_(center_d), security_(security), samples_(samples), g_(nullptr) {}
+  ~FastGaussianNoise() { if (g_) nflgpu_gaussian_destroy(g_); }
+  nflgpu_gaussian *handle(nflgpu_ctx *ctx) {
+    if (!g_ && nflgpu_gaussian_create(&g_, ctx, sigma_, security_, samples_, center_, (int)sizeof(in_class), (int)_lu_depth) != NFLGPU_OK)
+      throw std::runtime_error(std::string("FastGaussianNoise: ") + nflgpu_last_error());
+    return g_;
+  }
+};
+template <class in_class, class out_class, unsigned _lu_depth> struct gaussian {
+  FastGaussianNoise<in_class, out_class, _lu_depth> *fg_prng;
+  uint64_t amplifier;
+  gaussian(FastGaussianNoise<in_class, out_class, _lu_depth> *prng) : fg_prng(prng), amplifier(1) {}
+  gaussian(FastGaussianNoise<in_class, out_class, _lu_depth> *prng, uint64_t amp) : fg_prng(prng), amplifier(amp) {}
 };
 
 namespace detail {
@@ -398,6 +429,7 @@ public:
   poly(non_uniform const &mode) { set(mode); }
   poly(hwt_dist const &mode) { set(mode); }
   poly(ZO_dist const &mode) { set(mode); }
+  template <class in_class, unsigned _lu_depth> poly(gaussian<in_class, T, _lu_depth> const &mode) { set(mode); }
   poly(value_type v, bool reduce_coeffs = true) { set(v, reduce_coeffs); }
   poly(std::initializer_list<value_type> values, bool reduce_coeffs = true) { set(values.begin(), values.end(), reduce_coeffs); }
   template <class It> poly(It first, It last, bool reduce_coeffs = true) { set(first, last, reduce_coeffs); }
@@ -456,7 +488,21 @@ public:
     fetch(b);
   }
 
+  /* core.hpp:291-325: a draw consumes a data-dependent number of nonces (getNoise refills); like the reference's PRNG state,
+   * not thread safe */
+  template <class in_class, unsigned _lu_depth> void set(gaussian<in_class, T, _lu_depth> const &mode) {
+    detail::prng_state &g = detail::prng_state::get();
+    detail::dev_buf<poly> b(1);
+    uint64_t used = 0;
+    nflgpu_ctx *ctx = backend_type::get().ctx;
+    detail::check(nflgpu_gaussian_sample(ctx, mode.fg_prng->handle(ctx), b.p, 1, mode.amplifier, g.key, g.nonce.load(), &used, nullptr),
+                  "nflgpu_gaussian_sample");
+    g.take(used);
+    fetch(b);
+  }
+
   /* assignment */
+  template <class in_class, unsigned _lu_depth> poly &operator=(gaussian<in_class, T, _lu_depth> const &mode) { set(mode); return *this; }
   poly &operator=(value_type v) { set(v); return *this; }
   poly &operator=(uniform const &mode) { set(mode); return *this; }
   poly &operator=(non_uniform const &mode) { set(mode); return *this; }
@@ -759,6 +805,15 @@ public:
   }
   void set_hwt(uint32_t hwt, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:355-392
     detail::check(nflgpu_hwt(ctx(), buf_.p, buf_.count, hwt, key, first_nonce, nullptr), "nflgpu_hwt");
+  }
+  // count successive poly::set(gaussian(&prng, amplifier)) draws (core.hpp:291-325); returns the nonces they consumed
+  template <class in_class, unsigned _lu_depth>
+  uint64_t set_gaussian(FastGaussianNoise<in_class, typename P::value_type, _lu_depth> &prng, uint64_t amplifier, const uint8_t key[32],
+                        uint64_t first_nonce) {
+    uint64_t used = 0;
+    detail::check(nflgpu_gaussian_sample(ctx(), prng.handle(ctx()), buf_.p, buf_.count, amplifier, key, first_nonce, &used, nullptr),
+                  "nflgpu_gaussian_sample");
+    return used;
   }
   void set_zo(uint8_t rho, const uint8_t key[32], uint64_t first_nonce) {  // core.hpp:338-349
     detail::check(nflgpu_zo(ctx(), buf_.p, buf_.count, rho, key, first_nonce, nullptr), "nflgpu_zo");

@@ -711,27 +711,53 @@ int nflgpu_gaussian_sample(nflgpu_ctx *ctx, const nflgpu_gaussian *g, void *dst,
   a.batch = (uint32_t)batch;
   a.wp = g->t.wp; a.in_bytes = (uint32_t)g->t.in_bytes; a.depth = (uint32_t)g->t.depth; a.lu_size = g->t.lu_size;
   a.barriers = g->d_barriers; a.lut = g->d_lut;
-  // a draw makes one call plus (usually at most) one refill: start with a window of two nonces per polynomial, widen if the
-  // chain runs out of it
-  for (uint64_t per_poly = 2; per_poly <= 64; per_poly *= 2) {
-    a.window = (uint32_t)(batch * per_poly + 16);
-    const size_t noise_bytes = (size_t)a.window * ctx->degree * sizeof(int32_t);
-    const size_t total = noise_bytes + (size_t)a.window * 4 + batch * 4 + 16;
+  if (words * g->t.in_bytes + 64 > GAUSS_SMEM_BUDGET) { set_error("degree too large for the Gaussian sampler's shared-memory keystream"); return NFLGPU_ERR_UNSUPPORTED; }
+  // Large batches go out in chunks that bound the scratch (the nonce chain simply continues from chunk to chunk).  Inside a
+  // chunk a draw makes one call plus (usually at most) one refill: the window holds two nonces per polynomial (+16); if
+  // the chain still runs out of it the chunk is halved.
+  const size_t per_cand = ctx->degree * sizeof(int32_t) + 4 + (size_t)words * 5;
+  size_t budget = (size_t)768 << 20;
+  if (const char *mb = std::getenv("NFLGPU_GAUSS_SCRATCH_MB")) budget = (size_t)std::strtoull(mb, nullptr, 10) << 20;  // testing aid
+  size_t chunk = budget / (2 * per_cand);
+  if (chunk == 0) chunk = 1;
+  if (chunk > 12000) chunk = 12000;  // the chain kernel keeps two jump tables of the window in shared memory
+  uint64_t total_used = 0;
+  for (size_t done = 0; done < batch;) {
+    const size_t nb = batch - done < chunk ? batch - done : chunk;
+    a.dst = static_cast<unsigned char *>(dst) + done * a.poly_bytes;
+    a.batch = (uint32_t)nb;
+    a.first_nonce = first_nonce + total_used;
+    a.window = (uint32_t)(nb * 2 + 16);
+    a.rows = a.window + 8;
+    if ((uint64_t)a.rows * words >= (1ull << 32)) { chunk = nb / 2 ? nb / 2 : 1; if (nb == 1) break; continue; }  // 32-bit evaluation indices
+    // scratch layout: result[2] | pos_val | cand_idx | cand_calls | chosen | pos_adv (rows of `pitch` bytes)
+    const size_t val_bytes = ((size_t)a.rows * words * 4 + 15) & ~(size_t)15, idx_bytes = ((size_t)a.window * ctx->degree * 4 + 15) & ~(size_t)15;
+    const size_t small_bytes = (((size_t)a.window * 4 + nb * 4) + 15) & ~(size_t)15, pitch = (words + 15) & ~(size_t)15;
+    const size_t bytes = 16 + val_bytes + idx_bytes + small_bytes + (size_t)a.rows * pitch;
     unsigned char *scratch = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), total, s));
-    a.cand_noise = reinterpret_cast<int32_t *>(scratch);
-    a.cand_calls = reinterpret_cast<uint32_t *>(scratch + noise_bytes);
+    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), bytes, s));
+    a.result = reinterpret_cast<uint64_t *>(scratch);
+    a.pos_val = reinterpret_cast<int32_t *>(scratch + 16);
+    a.cand_idx = reinterpret_cast<uint32_t *>(scratch + 16 + val_bytes);
+    a.cand_calls = reinterpret_cast<uint32_t *>(scratch + 16 + val_bytes + idx_bytes);
     a.chosen = a.cand_calls + a.window;
-    a.result = reinterpret_cast<uint64_t *>(scratch + ((noise_bytes + (size_t)a.window * 4 + batch * 4 + 7) & ~(size_t)7));
-    cudaError_t e = launch_gaussian(a, s);
+    a.pos_adv = scratch + 16 + val_bytes + idx_bytes + small_bytes;  // 16-byte aligned: every part before it is a multiple of 16
+    cudaError_t e = launch_gaussian(a, ctx->device, ctx->num_sms, s);
     uint64_t result[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(result, a.result, sizeof(result), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFreeAsync(scratch, s);
     CUDA_TRY(e);
-    ctx->launches += 3;
-    if (result[1] == 0) {
-      if (nonces_used) *nonces_used = result[0];
+    ctx->launches += 4;
+    if (result[1] != 0) {  // the chain left the window (more than two nonces per draw on average): retry with fewer polynomials
+      if (nb == 1) break;
+      chunk = nb / 2;
+      continue;
+    }
+    total_used += result[0];
+    done += nb;
+    if (done == batch) {
+      if (nonces_used) *nonces_used = total_used;
       return NFLGPU_OK;
     }
   }

@@ -10,6 +10,7 @@
 namespace nflgpu {
 
 enum { GAUSS_MAX_ROW_BYTES = 64 };  // bytes of one barrier = precision of the cumulative distribution (512 bits)
+enum { GAUSS_WALK_THREADS = 32, GAUSS_SMEM_BUDGET = 200 * 1024 };
 
 // One look-up entry.  sub: -1 = not flagged; first level, depth 2: number of the second-level table (>= 1);
 // otherwise 0 = flagged, walk barriers [bstart, bstart + bcount).
@@ -44,14 +45,17 @@ struct GaussArgs {
   uint32_t wp, in_bytes, depth, lu_size;
   const unsigned char *barriers;
   const GaussLutEntry *lut;
-  // scratch: one candidate per possible starting nonce first_nonce + c, c < window
-  uint32_t window;
-  int32_t *cand_noise;   // [window][degree] signed outputs of getNoise()
-  uint32_t *cand_calls;  // [window] fastrandombytes calls the draw starting at that nonce makes
+  // scratch.  rows = window + a few: every nonce first_nonce + r, r < rows, gets its keystream evaluated at every position
+  uint32_t window, rows;
+  int32_t *pos_val;      // [rows][words_per_fill] output of an evaluation starting at that position
+  uint8_t *pos_adv;      // [rows][pitch] look-up words it consumes; pitch = words_per_fill rounded up to 16, base 16-byte aligned
+  uint32_t *cand_idx;    // [degree][window] where in pos_val output k of the draw starting at nonce first_nonce + c was evaluated
+  uint32_t *cand_calls;  // [window] fastrandombytes calls that draw makes
   uint32_t *chosen;      // [batch] candidate of polynomial b
   uint64_t *result;      // [0] = nonces consumed by the batch, [1] = 1 when the window was too small
+  uint32_t walk_rows, walk_stride;  // set by the launcher
 };
-cudaError_t launch_gaussian(const GaussArgs &a, cudaStream_t stream);
+cudaError_t launch_gaussian(GaussArgs a, int device, int num_sms, cudaStream_t stream);
 #endif
 
 }  // namespace nflgpu

@@ -205,106 +205,190 @@ __global__ void __launch_bounds__(256) uniform_kernel(const SampleArgs a) {
 
 // ---- poly::set(gaussian) core.hpp:291-325 over FastGaussianNoise::getNoise (prng/FastGaussianNoise.hpp:478-613) ----------
 //
-// getNoise() is sequential inside a polynomial (every output consumes 1, 2 or word_precision look-up words of one keystream)
-// and, across polynomials, the NONCE a draw starts with depends on how many times the draws before it refilled their buffer
-// (refills are data dependent, :601-610).  Three kernels keep the batch parallel and the result bit-identical:
-//   1. gauss_candidates: thread c runs the complete draw that would start at nonce first_nonce + c, for every c of a window
-//      (about 2 x batch: a draw makes one call plus, typically, at most one refill) and records its outputs and its number
-//      of fastrandombytes calls;
-//   2. gauss_chain: one thread follows nonce -> nonce + calls(nonce) from first_nonce: the candidates the reference's
-//      sequential draws really are;
-//   3. gauss_expand: coalesced copy of the chosen candidates into the batch, amplified, negative values stored as p + v in
-//      every residue.
-struct NoiseStream {  // look-up words of the keystream (key, nonce), generated 64 bytes at a time
-  const uint32_t (&key)[8];
-  uint64_t nonce, blk;
-  uint32_t x[16];
-  uint32_t in_bytes;
-  __device__ NoiseStream(const uint32_t (&k)[8], uint32_t ib) : key(k), nonce(0), blk(~0ull), in_bytes(ib) {}
-  __device__ void reset(uint64_t n) { nonce = n; blk = ~0ull; }
-  __device__ uint32_t word(uint64_t j) {
-    const uint64_t byte = j * in_bytes, b = byte >> 6;
-    if (b != blk) { blk = b; salsa20_block(key, nonce, b, x); }
-    const uint32_t o = (uint32_t)byte & 63u, w = x[o >> 2] >> (8 * (o & 3));
-    return in_bytes == 1 ? (w & 0xffu) : (w & 0xffffu);  // 16-bit words never straddle a 32-bit word: o is even
+// getNoise() is sequential twice over: inside a polynomial every output consumes 1, 2 or word_precision look-up words of one
+// keystream, so where an output starts depends on all outputs before it; and across polynomials the NONCE a draw starts with
+// depends on how many times the draws before it refilled their buffer (refills are data dependent, :601-610).  Both chains
+// are turned into "evaluate every possible start in parallel, then follow the chain":
+//   1. gauss_positions: for every nonce n of a window and EVERY position j of its keystream buffer, the output an evaluation
+//      starting at j would produce and the words it would consume (one CTA per nonce: Salsa20 blocks into shared memory,
+//      then one look-up evaluation per thread and position);
+//   2. gauss_walk: thread c follows position -> position + consumed for the draw that would start at nonce first_nonce + c
+//      (the consumed-words rows of its nonces are staged in shared memory, so a step is one shared-memory load and one
+//      fire-and-forget store: no global load sits on the chain), records WHERE each of the draw's outputs was evaluated
+//      and the draw's number of fastrandombytes calls;
+//   3. gauss_chain: one thread follows nonce -> nonce + calls(nonce) from first_nonce: the candidates the reference's
+//      sequential draws really are (calls staged in shared memory);
+//   4. gauss_expand: gathers the outputs of the chosen candidates into the batch, amplified, negative values stored as
+//      p + v in every residue (coalesced stores).
+__global__ void __launch_bounds__(128) gauss_positions_kernel(const GaussArgs a) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  uint32_t *ks = reinterpret_cast<uint32_t *>(gsm);  // keystream of this nonce, whole 64-byte blocks
+  const uint32_t row = blockIdx.x;                   // nonce first_nonce + row
+  const uint32_t words = (uint32_t)a.words_per_fill, wp = a.wp, depth = a.depth, ib = a.in_bytes;
+  const uint32_t nblk = (words * ib + 63) / 64;
+  for (uint32_t blk = threadIdx.x; blk < nblk; blk += blockDim.x) {
+    uint32_t x[16];
+    salsa20_block(a.key, a.first_nonce + row, blk, x);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ks[blk * 16 + i] = x[i];
   }
-};
-
-__global__ void __launch_bounds__(64) gauss_candidates_kernel(const GaussArgs a) {
-  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= a.window) return;
-  const uint64_t degree = 1ull << a.log2_degree;
-  const uint32_t wp = a.wp, depth = a.depth;
-  int32_t *out = a.cand_noise + (uint64_t)c * degree;
-  NoiseStream ns(a.key, a.in_bytes);
-  uint64_t nonce = a.first_nonce + c, pos = 0, used = 0;
-  uint32_t calls = 1;
-  ns.reset(nonce++);
-  for (uint64_t k = 0; k < degree; ++k) {
-    const uint32_t in1 = ns.word(pos);
-    GaussLutEntry e = a.lut[in1];
-    const bool flagged1 = e.sub >= 0;
-    if (flagged1 && depth == 2) e = a.lut[(uint64_t)e.sub * a.lu_size + ns.word(pos + 1)];
-    int32_t output = e.val;
-    if (e.sub >= 0) {  // walk the barriers of this entry: +1 for every barrier not above the noise (cmp(), :617-628)
-      uint32_t nw[GAUSS_MAX_ROW_BYTES];
-      for (uint32_t j = 0; j < wp; ++j) nw[j] = ns.word(pos + j);
-      for (uint32_t b = e.bstart; b < e.bstart + e.bcount; ++b) {
-        const unsigned char *row = a.barriers + (uint64_t)b * wp * a.in_bytes;
-        int cmp = 0;
-        for (uint32_t j = 0; j < wp && cmp == 0; ++j) {
-          const uint32_t bw = a.in_bytes == 1 ? row[j] : (uint32_t)row[2 * j] | ((uint32_t)row[2 * j + 1] << 8);
-          cmp = bw > nw[j] ? 1 : (bw < nw[j] ? -1 : 0);
+  __syncthreads();
+  auto word = [&](uint32_t j) -> uint32_t {
+    const uint32_t byte = j * ib, w = ks[byte >> 2] >> (8 * (byte & 3));
+    return ib == 1 ? (w & 0xffu) : (w & 0xffffu);  // 16-bit words never straddle a 32-bit word
+  };
+  int32_t *val = a.pos_val + (uint64_t)row * words;
+  uint8_t *adv = a.pos_adv + (uint64_t)row * a.walk_stride;
+  for (uint32_t j = threadIdx.x; j < words; j += blockDim.x) {
+    int32_t output = 0;
+    uint32_t consumed = 1;
+    if (j + wp < words) {  // getNoise() only ever starts an output where a full-precision comparison still fits (:601)
+      GaussLutEntry e = a.lut[word(j)];
+      const bool flagged1 = e.sub >= 0;
+      if (flagged1 && depth == 2) { e = a.lut[(uint64_t)e.sub * a.lu_size + word(j + 1)]; consumed = 2; }
+      output = e.val;
+      if (e.sub >= 0) {  // walk the barriers of this entry: +1 for every barrier not above the noise (cmp(), :617-628)
+        for (uint32_t b = e.bstart; b < e.bstart + e.bcount; ++b) {
+          const unsigned char *brow = a.barriers + (uint64_t)b * wp * ib;
+          int cmp = 0;
+          for (uint32_t i = 0; i < wp && cmp == 0; ++i) {
+            const uint32_t bw = ib == 1 ? brow[i] : (uint32_t)brow[2 * i] | ((uint32_t)brow[2 * i + 1] << 8), nw = word(j + i);
+            cmp = bw > nw ? 1 : (bw < nw ? -1 : 0);
+          }
+          if (cmp == 1) break;
+          ++output;
         }
-        if (cmp == 1) break;
-        ++output;
+        consumed = wp;
       }
-      pos += wp - depth; used += wp - depth;
     }
-    if (flagged1 && depth == 2) { ++pos; ++used; }
-    ++pos; ++used;
-    out[k] = output;
-    if (used + wp >= a.words_per_fill) {  // :601-610
-      pos = 0; used = 0;
-      ns.reset(nonce++);
-      ++calls;
+    val[j] = output;
+    adv[j] = (uint8_t)consumed;
+  }
+}
+
+__global__ void __launch_bounds__(GAUSS_WALK_THREADS) gauss_walk_kernel(const GaussArgs a) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const uint32_t words = (uint32_t)a.words_per_fill, wp = a.wp, stride = a.walk_stride, rows = a.rows, window = a.window;
+  const uint32_t c0 = blockIdx.x * blockDim.x, staged = a.walk_rows;  // rows c0 .. c0 + staged - 1 live in shared memory
+  const uint8_t *__restrict__ adv = a.pos_adv;
+  {  // rows have the same 16-byte-multiple pitch in global and in shared memory: one flat vector copy
+    const uint32_t nrows = c0 + staged <= rows ? staged : (c0 < rows ? rows - c0 : 0);
+    const uint4 *src = reinterpret_cast<const uint4 *>(adv + (uint64_t)c0 * stride);
+    uint4 *dst = reinterpret_cast<uint4 *>(gsm);
+    for (uint32_t i = threadIdx.x; i < nrows * (stride / 16); i += blockDim.x) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const uint32_t c = c0 + threadIdx.x;
+  if (c >= window) return;
+  const uint32_t degree = 1u << a.log2_degree;
+  // output k of candidate c goes to cand_idx[k][c]: the 32 candidates of a warp write one 128-byte line per step
+  uint32_t *__restrict__ out = a.cand_idx + c;
+  uint32_t n = c, pos = 0, calls = 1;
+  const unsigned char *row = gsm + (size_t)threadIdx.x * stride;  // row of nonce n while it is staged
+  bool in_smem = true;
+  for (uint32_t k = 0; k < degree; ++k) {
+    if (n >= rows) { calls = 0x40000000u; break; }  // ran past the evaluated nonces: the chain treats it as "window too small"
+    out[(uint64_t)k * window] = n * words + pos;      // index into pos_val (rows * words < 2^32: the caller's chunking bounds it)
+    pos += in_smem ? row[pos] : __ldg(adv + (uint64_t)n * stride + pos);
+    if (pos + wp >= words) {                          // :601-610: a fresh buffer from the next nonce
+      pos = 0; ++n; ++calls;
+      in_smem = n - c0 < staged;
+      row += stride;
     }
   }
   a.cand_calls[c] = calls;
 }
 
-__global__ void gauss_chain_kernel(const GaussArgs a) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  uint64_t at = 0;
-  uint32_t b = 0;
-  for (; b < a.batch && at < a.window; ++b) { a.chosen[b] = (uint32_t)at; at += a.cand_calls[at]; }
-  a.result[0] = at;
-  a.result[1] = b < a.batch ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(256) gauss_expand_kernel(const GaussArgs a) {
-  const uint64_t degree = 1ull << a.log2_degree, total = (uint64_t)a.batch << a.log2_degree;
-  const uint64_t wrap = a.limb_bits == 64 ? ~0ull : ((1ull << a.limb_bits) - 1);
-  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t poly = t >> a.log2_degree, i = t & (degree - 1);
-    // rnd[i] is signed_value_type: getNoise stores the low limb_bits of the output, rnd *= amplifier wraps at the limb width
-    uint64_t v = (uint64_t)(int64_t)a.cand_noise[(uint64_t)a.chosen[poly] * degree + i] & wrap;
-    if (a.amplifier != 1) v = (v * a.amplifier) & wrap;
-    const bool neg = (v >> (a.limb_bits - 1)) & 1;
-    for (uint32_t cm = 0; cm < a.nmoduli; ++cm)
-      store_any(reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes, a.limb_bits, (uint64_t)cm * degree + i,
-                (neg ? a.moduli[cm] + v : v) & wrap);
+// The nonce chain by pointer jumping: J_k[i] = where the chain is 2^k draws after nonce index i (index `window` absorbs
+// everything that leaves the window).  With chosen[0 .. 2^k) known, chosen[b + 2^k] = J_k[chosen[b]]; then J_{k+1} = J_k o J_k.
+// log2(batch) + 1 rounds of fully parallel shared-memory work instead of batch dependent steps.
+__global__ void __launch_bounds__(1024) gauss_chain_kernel(const GaussArgs a) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const uint32_t W = a.window;
+  uint32_t *J = reinterpret_cast<uint32_t *>(gsm), *K = J + (W + 1);
+  for (uint32_t i = threadIdx.x; i <= W; i += blockDim.x) {
+    uint64_t v = W;
+    if (i < W) { v = (uint64_t)i + a.cand_calls[i]; if (v > W) v = W; }
+    J[i] = (uint32_t)v;
+  }
+  if (threadIdx.x == 0) a.chosen[0] = 0;
+  __syncthreads();
+  for (uint32_t len = 1; len < a.batch; len <<= 1) {
+    for (uint32_t b = threadIdx.x; b < len && b + len < a.batch; b += blockDim.x) a.chosen[b + len] = J[a.chosen[b]];
+    for (uint32_t i = threadIdx.x; i <= W; i += blockDim.x) K[i] = J[J[i]];
+    __syncthreads();
+    uint32_t *t = J; J = K; K = t;
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t last = a.chosen[a.batch - 1];
+    const uint32_t calls = last < W ? a.cand_calls[last] : 0x40000000u;
+    a.result[0] = (uint64_t)last + calls;
+    a.result[1] = calls >= 0x40000000u ? 1 : 0;
   }
 }
 
-cudaError_t launch_gaussian(const GaussArgs &a, cudaStream_t stream) {
+// One CTA = 32 polynomials x 32 coefficients: the evaluation indices are read along the polynomial axis (cand_idx[k][c] with
+// c = chosen[poly], nearly consecutive), the values are gathered from pos_val, and the tile is written along the coefficient
+// axis (32 consecutive limbs of one residue row per warp store).
+__global__ void __launch_bounds__(1024) gauss_expand_kernel(const GaussArgs a) {
+  __shared__ int32_t tile[32][33];
+  const uint32_t degree = 1u << a.log2_degree, window = a.window;
+  const uint64_t wrap = a.limb_bits == 64 ? ~0ull : ((1ull << a.limb_bits) - 1);
+  const uint32_t tiles_i = degree / 32 ? degree / 32 : 1, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const uint32_t ntiles = ((a.batch + 31) / 32) * tiles_i;
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint32_t p0 = (t / tiles_i) * 32, i0 = (t % tiles_i) * 32;
+    {  // tx runs over polynomials, ty over coefficients
+      const uint32_t poly = p0 + tx, i = i0 + ty;
+      int32_t v = 0;
+      if (poly < a.batch && i < degree) v = a.pos_val[a.cand_idx[(uint64_t)i * window + min(a.chosen[poly], window - 1)]];
+      tile[ty][tx] = v;
+    }
+    __syncthreads();
+    {  // tx runs over coefficients, ty over polynomials
+      const uint32_t poly = p0 + ty, i = i0 + tx;
+      if (poly < a.batch && i < degree) {
+        // rnd[i] is signed_value_type: getNoise stores the low limb_bits of the output, rnd *= amplifier wraps at the limb width
+        uint64_t v = (uint64_t)(int64_t)tile[tx][ty] & wrap;
+        if (a.amplifier != 1) v = (v * a.amplifier) & wrap;
+        const bool neg = (v >> (a.limb_bits - 1)) & 1;
+        for (uint32_t cm = 0; cm < a.nmoduli; ++cm)
+          store_any(reinterpret_cast<unsigned char *>(a.dst) + (uint64_t)poly * a.poly_bytes, a.limb_bits, (uint64_t)cm * degree + i,
+                    (neg ? a.moduli[cm] + v : v) & wrap);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_gaussian(GaussArgs a, int device, int num_sms, cudaStream_t stream) {
   if (a.batch == 0) return cudaSuccess;
-  gauss_candidates_kernel<<<(a.window + 63) / 64, 64, 0, stream>>>(a);
-  gauss_chain_kernel<<<1, 32, 0, stream>>>(a);
-  const uint64_t total = (uint64_t)a.batch << a.log2_degree;
-  uint64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  gauss_expand_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a);
+  const uint32_t words = (uint32_t)a.words_per_fill;
+  static bool attr_set_dev[64] = {false};  // per device; racing first calls set the same values
+  if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+  bool &attr_set = attr_set_dev[device];
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gauss_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAUSS_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gauss_positions_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAUSS_SMEM_BUDGET);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gauss_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAUSS_SMEM_BUDGET);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const size_t ks_bytes = (size_t)((words * a.in_bytes + 63) / 64) * 64;
+  if (ks_bytes > GAUSS_SMEM_BUDGET) return cudaErrorInvalidValue;  // the launcher's caller checks this bound first
+  a.walk_stride = (words + 15) & ~15u;  // pitch of a pos_adv row, in global and in shared memory
+  gauss_positions_kernel<<<a.rows, 128, ks_bytes, stream>>>(a);
+  // rows of consumed-words staged per walk CTA: its own candidates' nonces plus two for refills, as many as fit
+  uint32_t staged = GAUSS_WALK_THREADS + 2;
+  if ((size_t)staged * a.walk_stride > GAUSS_SMEM_BUDGET) staged = (uint32_t)(GAUSS_SMEM_BUDGET / a.walk_stride);
+  a.walk_rows = staged;
+  gauss_walk_kernel<<<(a.window + GAUSS_WALK_THREADS - 1) / GAUSS_WALK_THREADS, GAUSS_WALK_THREADS, (size_t)staged * a.walk_stride, stream>>>(a);
+  if ((size_t)(a.window + 1) * 8 > GAUSS_SMEM_BUDGET) return cudaErrorInvalidValue;  // the caller's chunking bounds the window
+  gauss_chain_kernel<<<1, 1024, (size_t)(a.window + 1) * 8, stream>>>(a);
+  const uint64_t degree = 1ull << a.log2_degree;
+  uint64_t tiles = (uint64_t)((a.batch + 31) / 32) * (degree / 32 ? degree / 32 : 1);
+  if (tiles > (uint64_t)num_sms * 8) tiles = (uint64_t)num_sms * 8;
+  gauss_expand_kernel<<<(unsigned)tiles, 1024, 0, stream>>>(a);
   return cudaGetLastError();
 }
 

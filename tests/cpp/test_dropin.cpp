@@ -10,6 +10,7 @@
 //   usage: test_dropin <u64|u32|u16> <in_a.bin> <in_b.bin> <count> <out.bin>
 #include <nfl_b200.hpp>
 
+#include <cmath>
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -182,6 +183,29 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
         weight += h != 0;
       }
       REQUIRE(weight == P::degree / 8);
+      // discrete Gaussian (tests/nfllib_demo_main_op.cpp:141-144,273-283): same small centred value in every residue, within the
+      // tail bound (14.4 sigma for these parameters), amplified draws are multiples of the amplifier, and the draws differ
+      {
+        nfl::FastGaussianNoise<uint8_t, T, 2> fg(3.19, 128, 1 << 14);
+        P g1{nfl::gaussian<uint8_t, T, 2>(&fg)}, g2 = nfl::gaussian<uint8_t, T, 2>(&fg, 2);
+        REQUIRE(!same(g1, g2));
+        double sum = 0, sq = 0;
+        for (size_t i = 0; i < P::degree; ++i) {
+          const T p0 = P::get_modulus(0);
+          const T a = g1(0, i), b = g2(0, i);
+          const long va = a <= 64 ? (long)a : -(long)(p0 - a), vb = b <= 128 ? (long)b : -(long)(p0 - b);
+          REQUIRE(va >= -47 && va <= 47 && vb >= -94 && vb <= 94 && vb % 2 == 0);
+          sum += va; sq += (double)va * va;
+          for (size_t cm = 1; cm < P::nmoduli; ++cm) {
+            const T pc = P::get_modulus(cm);
+            REQUIRE(va >= 0 ? g1(cm, i) == a : pc - g1(cm, i) == p0 - a);
+            REQUIRE(vb >= 0 ? g2(cm, i) == b : pc - g2(cm, i) == p0 - b);
+          }
+        }
+        const double mean = sum / P::degree, var = sq / P::degree - mean * mean;
+        REQUIRE(std::fabs(mean) < 6 * 3.19 / std::sqrt((double)P::degree) + 1e-9);
+        if (P::degree >= 512) REQUIRE(var > 0.6 * 3.19 * 3.19 && var < 1.5 * 3.19 * 3.19);
+      }
       bool threw2 = false;
       try { P bad{nfl::non_uniform(P::get_modulus(0))}; (void)bad; } catch (std::runtime_error const &) { threw2 = true; }
       REQUIRE(threw2);                                          // core.hpp:201-206

@@ -130,6 +130,22 @@ def test_device_gaussian_matches_fixture_and_oracle(name):
 
 
 @pytest.mark.gpu
+def test_device_gaussian_large_batch_goes_out_in_chunks(monkeypatch):
+    """Batches whose scratch would exceed the budget are processed chunk by chunk; the nonce chain continues across chunks."""
+    z, meta = fixture()
+    m = meta["demo_u64"]
+    monkeypatch.setenv("NFLGPU_GAUSS_SCRATCH_MB", "4")  # ~137 polynomials per chunk for this shape
+    ctx = capi.Context(m["bits"], m["N"], m["M"])
+    t = table_of(z, "demo_u64", m)
+    g = capi.Gaussian(ctx, in_bytes=1, lu_depth=2, barriers=t.barriers, rounded_center=0)
+    want, calls = Oracle(m["bits"], m["N"], m["M"]).gaussian(1000, t, 1, Ref.FIXED_KEY, 77)
+    got, used = device_draws(ctx, g, 1000, Ref.FIXED_KEY, 77, 1)
+    assert used == calls and np.array_equal(got, want)
+    g.close()
+    ctx.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 def test_device_gaussian_next_to_the_live_reference():
     """The demo's shape (tests/nfllib_demo_main_op.cpp:141-144, 273-283): FastGaussianNoise<uint8_t, uint64_t, 2>(20, 128, 2^14),
