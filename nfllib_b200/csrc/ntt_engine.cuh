@@ -139,6 +139,19 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
                : "memory");
 }
 
+// L2 prefetch of the slab the slot will work on next (static unit walk only: the next index is known a whole unit ahead).
+// One 128-byte line per thread and request; the later LDGs then come from L2 instead of HBM.
+template <class C> __device__ __forceinline__ void prefetch_unit(const typename C::Store *slab, int tl) {
+#if !defined(NFLGPU_PREFETCH) || NFLGPU_PREFETCH
+  constexpr int LINES = (int)(C::B * sizeof(typename C::Store) / 128);
+#pragma unroll
+  for (int j = 0; j < (LINES + C::TPU - 1) / C::TPU; ++j) {
+    const int line = tl + j * C::TPU;
+    if (line < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(slab) + (size_t)line * 128));
+  }
+#endif
+}
+
 template <class C> __device__ __forceinline__ void unit_sync(int slot, int lane_base) {
   if (C::TPU >= 64) {
     if (C::SLOTS == 1) __syncthreads();
@@ -345,12 +358,11 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
 
 // ---- pass chains (compile-time recursion over the passes) ---------------------------------------------------
 
-// forward: passes SPLIT+1 .. NP-1 after pass SPLIT has stored its result into the tile
+// forward: passes SPLIT+1 .. NP-1 after pass SPLIT has stored its result into the tile (the caller has synchronised the slot)
 template <class C, int PASS> struct FwdChain {
   static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
                                              typename C::Word p, typename C::Word np, typename C::Word twop, int tid, int slot,
                                              int lane_base) {
-    unit_sync<C>(slot, lane_base);
     tile_load<C, PASS>(x, tile, tid);
     fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
     if (PASS == C::NP - 1) {
@@ -358,6 +370,7 @@ template <class C, int PASS> struct FwdChain {
       for (int k = 0; k < C::E; ++k) x[k] = fwd_canon<C>(x[k], p, twop);
     }
     tile_store<C, PASS>(x, tile, tid);
+    if (PASS + 1 < C::NP) unit_sync<C>(slot, lane_base);
     FwdChain<C, PASS + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
   }
 };
@@ -366,15 +379,16 @@ template <class C> struct FwdChain<C, C::NP> {
                                              typename C::Word, typename C::Word, int, int, int) {}
 };
 
-// inverse: passes NP-1 .. SPLIT+1 (tile -> registers -> tile); pass SPLIT is done by the kernel body
+// inverse: passes NP-1 .. SPLIT+1 (tile -> registers -> tile) after the caller has synchronised the slot; pass SPLIT is
+// done by the kernel body
 template <class C, int PASS> struct InvChain {
   static __device__ __forceinline__ void run(typename C::Word (&x)[C::E], typename C::Word *tile, const typename C::TW *tw,
                                              typename C::Word p, typename C::Word np, typename C::Word twop, const typename C::TW ninv,
                                              int tid, int slot, int lane_base) {
-    unit_sync<C>(slot, lane_base);
     tile_load<C, PASS>(x, tile, tid);
     inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, np, twop, ninv);
     tile_store<C, PASS>(x, tile, tid);
+    if (PASS - 1 > C::SPLIT) unit_sync<C>(slot, lane_base);
     InvChain<C, PASS - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
   }
 };
@@ -413,6 +427,13 @@ template <class C> struct UnitWalk {
     }
   }
   __device__ __forceinline__ uint32_t index() const { return cur; }
+  // The index of the NEXT iteration, for prefetching: known at once in the static walk; in the dynamic walk the leader
+  // publishes its claim through the mailbox (call publish() before a slot barrier that is late enough for the atomic to have
+  // returned, peek_next() after it; advance() rewrites the same value).
+  __device__ __forceinline__ void publish() {
+    if (C::DYNAMIC && !C::CLAIM_LATE && leader) box[par] = ahead;
+  }
+  __device__ __forceinline__ uint32_t peek_next() const { return C::DYNAMIC ? (C::CLAIM_LATE ? 0xffffffffu : box[par]) : cur + stride; }
   // call at the top of an iteration
   __device__ __forceinline__ void claim_ahead() {
     if (C::DYNAMIC && !C::CLAIM_LATE && leader) ahead = claim(cnt);
@@ -441,6 +462,14 @@ template <class C> struct UnitWalk {
     }
   }
 };
+
+// L2 prefetch of the sub-block the slot transforms in its next iteration (measured on B200, gpurun_out/variants.log round 1e:
+// -1 .. -4 % per launch; the unit's first loads otherwise wait for HBM with nothing of their own warp to overlap)
+template <class C> __device__ __forceinline__ void next_unit_prefetch(const UnitWalk<C> &walk, const typename C::Store *src, uint32_t nmoduli,
+                                                                      int cm, uint32_t nblocks, int tl) {
+  const uint32_t jn = walk.peek_next();
+  if (jn < nblocks) prefetch_unit<C>(src + ((size_t)(jn >> C::LOGG) * nmoduli + cm) * C::N + (size_t)(jn & ((1u << C::LOGG) - 1)) * C::B, tl);
+}
 
 // ---- kernels -------------------------------------------------------------------------------------------------
 
@@ -489,6 +518,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     const uint32_t b = j >> C::LOGG, g = j & ((1u << C::LOGG) - 1);
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
     const int tid = (int)(g * C::TPU) + tl;  // index inside the whole unit
+    if (!C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // static walk: the next index is known now
     Word x[C::E];
     // the first tile pass reads straight from global memory: for fixed k the threads touch consecutive limbs
 #pragma unroll
@@ -505,6 +535,9 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
       const size_t bbase = ubase + (size_t)g * C::B;
       if (!C::DYNAMIC) unit_sync<C>(slot, lane_base);  // previous sub-block's copy-out has finished reading the tile (advance() syncs in dynamic mode)
       tile_store<C, S>(x, tile, tid);
+      walk.publish();
+      unit_sync<C>(slot, lane_base);
+      if (C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // the leader's claim has just been published
       FwdChain<C, S + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
       if (MUL) tile_to_gmem_mul<C, LB>(tile, dst + bbase, reinterpret_cast<const Store *>(a.other) + bbase, tl, p, a.consts[cm]);
@@ -540,6 +573,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     const uint32_t b = j >> C::LOGG, g = j & ((1u << C::LOGG) - 1);
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
     const int tid = (int)(g * C::TPU) + tl;
+    if (!C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);
     Word x[C::E];
     if (C::NP - S == 1) {
 #pragma unroll
@@ -547,6 +581,9 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     } else {
       if (!C::DYNAMIC) unit_sync<C>(slot, lane_base);  // previous sub-block's last pass has finished reading the tile (advance() syncs in dynamic mode)
       gmem_to_tile<C>(tile, src + ubase + (size_t)g * C::B, tl);
+      walk.publish();
+      unit_sync<C>(slot, lane_base);
+      if (C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);
       InvChain<C, C::NP - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
       tile_load<C, S>(x, tile, tid);

@@ -1,5 +1,7 @@
 cd /root/repo
-timeout 600 python -m pytest tests/test_gaussian.py -m gpu -x -q 2>&1 | tail -8
-timeout 120 python tools/gauss_bench.py 2>&1 | tail -4
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/gauss_launches.csv python tools/gauss_bench.py > gpurun_out/gauss_ncu.log 2>&1
-grep -v "^==" gpurun_out/gauss_launches.csv | awk -F'","' '{print $5, $NF}' | tail -8
+N="nfllib_b200/libnflgpu.so"
+tools/gpu_variants.sh "--bits 64 --degree 1024 --nmoduli 4 --batch 4096" $N build/variants/nopf10/libnflgpu.so $N build/variants/nopf10/libnflgpu.so
+tools/gpu_variants.sh "--bits 64 --degree 8192 --nmoduli 6 --batch 2048" $N build/variants/nopf13/libnflgpu.so
+tools/gpu_variants.sh "--bits 64 --degree 16384 --nmoduli 8 --batch 1024" $N build/variants/nopf14/libnflgpu.so
+tools/gpu_variants.sh "--bits 32 --degree 4096 --nmoduli 14 --batch 2048" $N build/variants/nopf12_32/libnflgpu.so
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -4

@@ -2,7 +2,7 @@
 # One GPU-box visit of the development loop: GPU suite, all-config kernel table, bench line, ncu launch list + full capture.
 # Results land in gpurun_out/ (copy what should be judged into profiles/).
 cd "$(dirname "$0")/.."
-TAG=${1:-r01d}
+TAG=${1:-r01e}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
