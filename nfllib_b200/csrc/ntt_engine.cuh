@@ -54,7 +54,7 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int E = 1 << e;
   // Forward butterflies of the 16-coefficient 64-bit kernels use the "top-bit" lazy range (modarith.cuh csub_top): values
   // anywhere in [0, 2^64), conditional subtract in four instructions instead of five.  Measured on B200
-  // (gpurun_out/variants.log, round 1e): N = 1024: 126.8 -> 124.1 us per launch; the 32-coefficient kernels (4 warps per
+  // (profiles/r01e_variants.log): N = 1024: 126.8 -> 124.1 us per launch; the 32-coefficient kernels (4 warps per
   // sub-partition) lose 10-13 % with it -- ptxas routes every predicated carry through one predicate register, which
   // serialises the sixteen conditional subtracts of a stage -- so they keep the [0, 4p) form.
 #if defined(NFLGPU_LAZY64)
@@ -463,7 +463,7 @@ template <class C> struct UnitWalk {
   }
 };
 
-// L2 prefetch of the sub-block the slot transforms in its next iteration (measured on B200, gpurun_out/variants.log round 1e:
+// L2 prefetch of the sub-block the slot transforms in its next iteration (measured on B200, profiles/r01e_variants.log:
 // -1 .. -4 % per launch; the unit's first loads otherwise wait for HBM with nothing of their own warp to overlap)
 template <class C> __device__ __forceinline__ void next_unit_prefetch(const UnitWalk<C> &walk, const typename C::Store *src, uint32_t nmoduli,
                                                                       int cm, uint32_t nblocks, int tl) {
