@@ -12,30 +12,7 @@
 
 namespace nflgpu {
 
-// ---- functors ------------------------------------------------------------------------------------------------
-
-template <int LB, int OP> struct Functor {
-  typedef typename PW<LB>::Word Word;
-  static __device__ __forceinline__ Word apply(Word a, Word b, Word c, Word d, Word p, uint64_t k) {
-    if (OP == PW_ADD) return csub(a + b, p);                               // ops.hpp:132-133
-    if (OP == PW_SUB) return csub(a + (p - b), p);                         // ops.hpp:149
-    if (OP == PW_MUL) return PW<LB>::mulmod(a, b, p, k);                   // ops.hpp:184-219
-    if (OP == PW_MUL_SHOUP) {                                              // ops.hpp:231-241
-      const Word q = PW<LB>::mulhi(a, c);
-      return csub((Word)(a * b - q * p), p);
-    }
-    if (OP == PW_COMPUTE_SHOUP) {                                          // ops.hpp:170-176
-      while (a >= p) a -= p;
-      return PW<LB>::shoup_of(a, p, k);
-    }
-    if (OP == PW_MULADD) return csub(a + PW<LB>::mulmod(b, c, p, k), p);   // a + b*c
-    if (OP == PW_MULADD_SHOUP) {                                           // a + shoup(b*c, c') (opt/ops.hpp:56-78)
-      const Word q = PW<LB>::mulhi(b, d);
-      return csub(a + csub((Word)(b * c - q * p), p), p);
-    }
-    return 0;
-  }
-};
+// (the functors themselves are in modmul.cuh: Functor<LB, OP>::apply, shared with the host simulation of the CPU suite)
 
 template <int LB> struct VecIO;
 template <> struct VecIO<64> {

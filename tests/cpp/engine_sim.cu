@@ -6,7 +6,8 @@
 // (tables.cpp).  What it checks, on the CPU suite, is everything of the kernels that is arithmetic or index algebra:
 // the pass plan, the lazy ranges (including the 64-bit "top-bit" forward scheme), the table layout and
 // the canonicalisation.  What it cannot check — launch geometry, tile padding, barriers, TMA — is covered by the GPU suite.
-// Results are compared with the oracle by tests/test_engine_sim.py.
+// The coefficient-wise functors of the pointwise kernels (modmul.cuh Functor<LB, OP>::apply, also used by the fused
+// forward-NTT * operand epilogue) are exposed the same way.  Results are compared with the oracle by tests/test_engine_sim.py.
 #include "../../nfllib_b200/csrc/host_common.hpp"
 #include "../../nfllib_b200/csrc/ntt_engine.cuh"
 
@@ -75,6 +76,26 @@ template <int LB, int LOGN> int sim_one(int inverse, uint64_t p, uint64_t root, 
 
 }  // namespace
 
+template <int LB, int OP> void pw_all(uint64_t p, uint64_t k, const uint64_t *a, const uint64_t *b, const uint64_t *c, const uint64_t *d,
+                                      uint64_t *out, size_t n) {
+  typedef typename PW<LB>::Word Word;
+  for (size_t i = 0; i < n; ++i)
+    out[i] = (uint64_t)Functor<LB, OP>::apply((Word)a[i], b ? (Word)b[i] : 0, c ? (Word)c[i] : 0, d ? (Word)d[i] : 0, (Word)p, k);
+}
+template <int LB> int pw_dispatch(int op, uint64_t p, uint64_t k, const uint64_t *a, const uint64_t *b, const uint64_t *c, const uint64_t *d,
+                                  uint64_t *out, size_t n) {
+  switch (op) {
+    case PW_ADD: pw_all<LB, PW_ADD>(p, k, a, b, c, d, out, n); return 0;
+    case PW_SUB: pw_all<LB, PW_SUB>(p, k, a, b, c, d, out, n); return 0;
+    case PW_MUL: pw_all<LB, PW_MUL>(p, k, a, b, c, d, out, n); return 0;
+    case PW_MUL_SHOUP: pw_all<LB, PW_MUL_SHOUP>(p, k, a, b, c, d, out, n); return 0;
+    case PW_COMPUTE_SHOUP: pw_all<LB, PW_COMPUTE_SHOUP>(p, k, a, b, c, d, out, n); return 0;
+    case PW_MULADD: pw_all<LB, PW_MULADD>(p, k, a, b, c, d, out, n); return 0;
+    case PW_MULADD_SHOUP: pw_all<LB, PW_MULADD_SHOUP>(p, k, a, b, c, d, out, n); return 0;
+  }
+  return -1;
+}
+
 #define SIM_CASE(LB, LOGN) \
   case LOGN: return sim_one<LB, LOGN>(inverse, p, root, kmax, data);
 
@@ -97,5 +118,15 @@ extern "C" int nflsim_ntt(int limb_bits, int log2_degree, int inverse, uint64_t 
       SIM_CASE(16, 4) SIM_CASE(16, 5) SIM_CASE(16, 6) SIM_CASE(16, 7) SIM_CASE(16, 8) SIM_CASE(16, 9)
     }
   }
+  return -1;
+}
+
+// One pointwise functor over n coefficients of one residue (operands widened to uint64_t; unused operands may be null).
+// op: PwOp of pointwise.h; the per-modulus constant is derived exactly as nflgpu_ctx_create derives it.
+extern "C" int nflsim_pointwise(int limb_bits, int op, uint64_t p, const uint64_t *a, const uint64_t *b, const uint64_t *c, const uint64_t *d,
+                                uint64_t *out, size_t n) {
+  if (limb_bits == 64) return pw_dispatch<64>(op, p, newton_pn(64, p), a, b, c, d, out, n);
+  if (limb_bits == 32) return pw_dispatch<32>(op, p, (uint64_t)((((unsigned __int128)1) << 64) / p), a, b, c, d, out, n);
+  if (limb_bits == 16) return pw_dispatch<16>(op, p, 0, a, b, c, d, out, n);
   return -1;
 }

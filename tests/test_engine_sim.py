@@ -23,7 +23,25 @@ def sim():
         _lib = ctypes.CDLL(SIM_SO)
         _lib.nflsim_ntt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                     ctypes.c_void_p]
+        _lib.nflsim_pointwise.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64] + [ctypes.c_void_p] * 5 + [ctypes.c_size_t]
     return _lib
+
+
+PW = {"add": 0, "sub": 1, "mul": 2, "mul_shoup": 3, "compute_shoup": 4, "muladd": 5, "muladd_shoup": 6}
+
+
+def run_pw(bits, M, op, a, b=None, c=None, d=None):
+    """Functor<LB, OP>::apply over whole polynomials [batch][M][N], residue by residue."""
+    g = golden_params(bits)
+    out = np.empty_like(a)
+    w = lambda x, cm: None if x is None else np.ascontiguousarray(x[:, cm].astype(np.uint64))
+    for cm in range(M):
+        ops = [w(x, cm) for x in (a, b, c, d)]
+        o = np.empty_like(ops[0])
+        rc = sim().nflsim_pointwise(bits, PW[op], g["P"][cm], *[None if x is None else x.ctypes.data for x in ops], o.ctypes.data, o.size)
+        assert rc == 0
+        out[:, cm] = o.astype(DTYPES[bits])
+    return out
 
 
 def run_sim(bits, N, M, polys, inverse):
@@ -67,3 +85,28 @@ def test_kernel_butterfly_networks_on_the_host_match_the_oracle(bits, N):
     assert np.array_equal(back, a)
     # the inverse on arbitrary canonical input (not only on forward outputs)
     assert np.array_equal(run_sim(bits, N, M, a, inverse=True), o.run("inv", a))
+
+
+@pytest.mark.parametrize("bits,N", [(64, 256), (32, 256), (16, 128)])
+def test_pointwise_functors_on_the_host_match_the_oracle(bits, N):
+    """addmod / submod / mulmod / mulmod_shoup / compute_shoup / muladd[_shoup] as the kernels compute them (modmul.cuh), on random
+    operands and on the extremes 0, 1, p-1."""
+    M = 2
+    o = Oracle(bits, N, M)
+    P = np.array(golden_params(bits)["P"][:M], dtype=np.uint64)
+    a = np.concatenate([random_polys(bits, N, M, 6, 91), edge_polys(bits, N, M)])
+    b = np.concatenate([random_polys(bits, N, M, 6, 92), edge_polys(bits, N, M)[::-1]])
+    c = np.concatenate([random_polys(bits, N, M, 6, 93), edge_polys(bits, N, M)])
+    for x in (a, b):  # sprinkle the extremes over the random part too
+        x[0, :, :8] = 0
+        x[1, :, :8] = 1
+        x[2, :, :8] = (P - 1)[:, None].astype(DTYPES[bits])
+    bs = o.run("compute_shoup", b)
+    assert np.array_equal(run_pw(bits, M, "compute_shoup", b), bs)
+    assert np.array_equal(run_pw(bits, M, "add", a, b), o.run("add", a, b))
+    assert np.array_equal(run_pw(bits, M, "sub", a, b), o.run("sub", a, b))
+    assert np.array_equal(run_pw(bits, M, "mul", a, b), o.run("mul", a, b))
+    assert np.array_equal(run_pw(bits, M, "mul_shoup", a, b, bs), o.run("mul_shoup", a, b, bs))
+    assert np.array_equal(run_pw(bits, M, "muladd", c, a, b), o.run("muladd", c, a, b))
+    # muladd_shoup(c, a, b, b') = c + a*b computed through the Shoup word: same value as muladd
+    assert np.array_equal(run_pw(bits, M, "muladd_shoup", c, a, b, bs), o.run("muladd", c, a, b))
