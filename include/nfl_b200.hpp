@@ -115,7 +115,7 @@ template <class T> constexpr unsigned int params<T>::kModulusRepresentationBitsi
 template <class T> constexpr unsigned int params<T>::kMaxPolyDegree;
 
 // The reference's backend seam is the SIMD tag chosen by CC_SIMD (arch.hpp:6-18); this backend's tag:
-namespace simd { struct cuda {}; }
+namespace simd { struct cuda {}; struct serial {}; }  // (serial: accepted where reference code names it, tests/nfllib_demo_main_op.cpp:79)
 #define CC_SIMD nfl::simd::cuda
 
 /* Generators to initialise random polynomials (poly.hpp:42-62).  All four are drawn ON THE DEVICE by the samplers of
@@ -246,7 +246,15 @@ template <class P> struct dev_buf {
 // ---------------------------------------------------------------------------------------------------------
 namespace ops {
 
-struct addmod {}; struct submod {}; struct mulmod {}; struct shoup {}; struct mulmod_shoup {}; struct compute_shoup {};
+// (class templates with the reference's parameter list <value type, SIMD tag> — ops.hpp:124-242 — so that reference code naming
+//  a functor explicitly, e.g. ops::make_op<ops::mulmod_shoup<T, simd::serial>>(a, b, b') in tests/nfllib_demo_main_op.cpp:79,
+//  compiles; the parameters select nothing here: every functor runs on the device)
+template <class T = void, class Tag = void> struct addmod {};
+template <class T = void, class Tag = void> struct submod {};
+template <class T = void, class Tag = void> struct mulmod {};
+template <class T = void, class Tag = void> struct mulmod_shoup {};
+template <class T = void, class Tag = void> struct compute_shoup {};
+struct shoup {};
 struct eqmod {}; struct neqmod {};
 
 template <class Op, class... Args> struct expr {
@@ -287,21 +295,21 @@ template <class T, size_t D, size_t M> struct operand_eval<poly<T, D, M>, poly_p
       return a;                                                                                                     \
     }                                                                                                               \
   };
-NFLB200_BIN(submod, nflgpu_sub)
-NFLB200_BIN(mulmod, nflgpu_mul)
+NFLB200_BIN(submod<>, nflgpu_sub)
+NFLB200_BIN(mulmod<>, nflgpu_mul)
 #undef NFLB200_BIN
 
 // x + y  — with the fused form when y is a product (core.hpp:24-37 evaluates the whole tree in one pass)
-template <class P, class A0, class A1> struct operand_eval<P, ops::expr<ops::addmod, A0, A1>> {
-  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::addmod, A0, A1> const &e) {
+template <class P, class A0, class A1> struct operand_eval<P, ops::expr<ops::addmod<>, A0, A1>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::addmod<>, A0, A1> const &e) {
     auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
     auto b = operand_eval<P, A1>::run(std::get<1>(e.args));
     check(nflgpu_add(P::backend_type::get().ctx, a->p, a->p, b->p, 1, nullptr), "nflgpu_add");
     return a;
   }
 };
-template <class P, class A0, class B0, class B1> struct operand_eval<P, ops::expr<ops::addmod, A0, ops::expr<ops::mulmod, B0, B1>>> {
-  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::addmod, A0, ops::expr<ops::mulmod, B0, B1>> const &e) {
+template <class P, class A0, class B0, class B1> struct operand_eval<P, ops::expr<ops::addmod<>, A0, ops::expr<ops::mulmod<>, B0, B1>>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::addmod<>, A0, ops::expr<ops::mulmod<>, B0, B1>> const &e) {
     auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
     auto const &m = std::get<1>(e.args);
     auto b = operand_eval<P, B0>::run(std::get<0>(m.args));
@@ -310,8 +318,8 @@ template <class P, class A0, class B0, class B1> struct operand_eval<P, ops::exp
     return a;
   }
 };
-template <class P, class A0, class A1, class A2> struct operand_eval<P, ops::expr<ops::mulmod_shoup, A0, A1, A2>> {
-  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::mulmod_shoup, A0, A1, A2> const &e) {
+template <class P, class A0, class A1, class A2> struct operand_eval<P, ops::expr<ops::mulmod_shoup<>, A0, A1, A2>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::mulmod_shoup<>, A0, A1, A2> const &e) {
     auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
     auto b = operand_eval<P, A1>::run(std::get<1>(e.args));
     auto c = operand_eval<P, A2>::run(std::get<2>(e.args));
@@ -319,8 +327,8 @@ template <class P, class A0, class A1, class A2> struct operand_eval<P, ops::exp
     return a;
   }
 };
-template <class P, class A0> struct operand_eval<P, ops::expr<ops::compute_shoup, A0>> {
-  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::compute_shoup, A0> const &e) {
+template <class P, class A0> struct operand_eval<P, ops::expr<ops::compute_shoup<>, A0>> {
+  static std::unique_ptr<dev_buf<P>> run(ops::expr<ops::compute_shoup<>, A0> const &e) {
     auto a = operand_eval<P, A0>::run(std::get<0>(e.args));
     check(nflgpu_compute_shoup(P::backend_type::get().ctx, a->p, a->p, 1, nullptr), "nflgpu_compute_shoup");
     return a;
@@ -354,18 +362,18 @@ template <class T, size_t D, size_t M> struct emit<poly<T, D, M>, poly_p<T, D, M
       emit<P, A0>::run(r, std::get<0>(e.args)); emit<P, A1>::run(r, std::get<1>(e.args)); r.op(TOK, 2); \
     }                                                                                            \
   };
-NFLB200_EMIT_BIN(addmod, 0x10)
-NFLB200_EMIT_BIN(submod, 0x11)
-NFLB200_EMIT_BIN(mulmod, 0x12)
+NFLB200_EMIT_BIN(addmod<>, 0x10)
+NFLB200_EMIT_BIN(submod<>, 0x11)
+NFLB200_EMIT_BIN(mulmod<>, 0x12)
 #undef NFLB200_EMIT_BIN
-template <class P, class A0, class A1, class A2> struct emit<P, ops::expr<ops::mulmod_shoup, A0, A1, A2>> {
-  static void run(rpn<P> &r, ops::expr<ops::mulmod_shoup, A0, A1, A2> const &e) {
+template <class P, class A0, class A1, class A2> struct emit<P, ops::expr<ops::mulmod_shoup<>, A0, A1, A2>> {
+  static void run(rpn<P> &r, ops::expr<ops::mulmod_shoup<>, A0, A1, A2> const &e) {
     emit<P, A0>::run(r, std::get<0>(e.args)); emit<P, A1>::run(r, std::get<1>(e.args)); emit<P, A2>::run(r, std::get<2>(e.args));
     r.op(0x13, 3);
   }
 };
-template <class P, class A0> struct emit<P, ops::expr<ops::compute_shoup, A0>> {
-  static void run(rpn<P> &r, ops::expr<ops::compute_shoup, A0> const &e) { emit<P, A0>::run(r, std::get<0>(e.args)); r.op(0x14, 1); }
+template <class P, class A0> struct emit<P, ops::expr<ops::compute_shoup<>, A0>> {
+  static void run(rpn<P> &r, ops::expr<ops::compute_shoup<>, A0> const &e) { emit<P, A0>::run(r, std::get<0>(e.args)); r.op(0x14, 1); }
 };
 
 // Evaluates `e` into host poly `out`: fused single kernel when the tree fits nflgpu_eval's limits, node by node otherwise.
@@ -699,20 +707,33 @@ using poly_p_from_modulus = poly_p<T, Degree, AggregatedModulusBitSize / params<
   template <class A0, class A1>                                                                                             \
   typename std::enable_if<detail::is_operand<A0>::value && detail::is_operand<A1>::value, ops::expr<ops::TAG, A0, A1>>::type \
   NAME(A0 const &a, A1 const &b) { return ops::expr<ops::TAG, A0, A1>(a, b); }
-NFLB200_DECLARE_BINARY(operator-, submod)
-NFLB200_DECLARE_BINARY(operator+, addmod)
-NFLB200_DECLARE_BINARY(operator*, mulmod)
+NFLB200_DECLARE_BINARY(operator-, submod<>)
+NFLB200_DECLARE_BINARY(operator+, addmod<>)
+NFLB200_DECLARE_BINARY(operator*, mulmod<>)
 NFLB200_DECLARE_BINARY(operator==, eqmod)
 NFLB200_DECLARE_BINARY(operator!=, neqmod)
 #undef NFLB200_DECLARE_BINARY
 
+// ops::make_op<Functor<T, Tag>>(args...) (ops.hpp:249-262): an expression node for an explicitly named functor
+namespace ops {
+template <class Op> struct node_tag;
+template <class T, class Tag> struct node_tag<addmod<T, Tag>> { typedef addmod<> type; };
+template <class T, class Tag> struct node_tag<submod<T, Tag>> { typedef submod<> type; };
+template <class T, class Tag> struct node_tag<mulmod<T, Tag>> { typedef mulmod<> type; };
+template <class T, class Tag> struct node_tag<mulmod_shoup<T, Tag>> { typedef mulmod_shoup<> type; };
+template <class T, class Tag> struct node_tag<compute_shoup<T, Tag>> { typedef compute_shoup<> type; };
+template <class Op, class... Args> expr<typename node_tag<Op>::type, Args...> make_op(Args const &... args) {
+  return expr<typename node_tag<Op>::type, Args...>(args...);
+}
+}  // namespace ops
+
 // shoup(a * b, bprime)  ->  mulmod_shoup(a, b, bprime)   (ops.hpp:266-277)
 template <class A0, class A1, class A2>
-ops::expr<ops::mulmod_shoup, A0, A1, A2> shoup(ops::expr<ops::mulmod, A0, A1> const &prod, A2 const &bprime) {
-  return ops::expr<ops::mulmod_shoup, A0, A1, A2>(std::get<0>(prod.args), std::get<1>(prod.args), bprime);
+ops::expr<ops::mulmod_shoup<>, A0, A1, A2> shoup(ops::expr<ops::mulmod<>, A0, A1> const &prod, A2 const &bprime) {
+  return ops::expr<ops::mulmod_shoup<>, A0, A1, A2>(std::get<0>(prod.args), std::get<1>(prod.args), bprime);
 }
-template <class A0> typename std::enable_if<detail::is_operand<A0>::value, ops::expr<ops::compute_shoup, A0>>::type compute_shoup(A0 const &a) {
-  return ops::expr<ops::compute_shoup, A0>(a);
+template <class A0> typename std::enable_if<detail::is_operand<A0>::value, ops::expr<ops::compute_shoup<>, A0>>::type compute_shoup(A0 const &a) {
+  return ops::expr<ops::compute_shoup<>, A0>(a);
 }
 
 namespace detail {
