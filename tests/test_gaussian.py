@@ -73,6 +73,25 @@ def test_oracle_and_product_tables_against_the_live_reference(cfg):
     assert np.array_equal(bar, t.barriers) and d["flag_ctr1"] == t.params["flag_ctr1"] and d["flag_ctr2"] == t.params["flag_ctr2"]
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_product_tables_equal_the_reference_tables_over_random_parameters():
+    """40 seeded (sigma, security, samples, center, in_class, depth) draws: barrier table, flag counters and rounded center of
+    nflgpu_gaussian_table equal the private members of the reference's FastGaussianNoise object."""
+    rng = np.random.default_rng(5)
+    for i in range(40):
+        sigma = float(np.round(rng.uniform(0.8, 400.0), 3)) if i % 3 else float(rng.integers(1, 60))
+        sec = int(rng.choice([64, 80, 100, 128, 192, 256]))
+        samples = int(1 << rng.integers(4, 24))
+        center = float(np.round(rng.uniform(-50, 50), 2)) if i % 2 else 0.0
+        ib, depth = [(1, 2), (1, 1), (2, 1)][i % 3]
+        if ib == 1 and sigma > 120:
+            sigma = sigma / 8
+        h, t = Ref.gaussian_table(sigma, sec, samples, center, ib, depth, 64)
+        d, bar = capi.gaussian_table(sigma, sec, samples, center, ib, depth)
+        assert bar.shape == t.barriers.shape and np.array_equal(bar, t.barriers), (sigma, sec, samples, center, ib, depth)
+        assert (d["flag_ctr1"], d["flag_ctr2"], d["rounded_center"]) == (t.params["flag_ctr1"], t.params["flag_ctr2"], t.rounded_center)
+
+
 def test_gaussian_argument_errors_are_reported_not_thrown():
     with pytest.raises(capi.NflGpuError):
         capi.gaussian_table(-1.0, 128, 1024)
