@@ -341,7 +341,12 @@ __global__ void __launch_bounds__(1024) gauss_expand_kernel(const GaussArgs a) {
     {  // tx runs over polynomials, ty over coefficients
       const uint32_t poly = p0 + tx, i = i0 + ty;
       int32_t v = 0;
-      if (poly < a.batch && i < degree) v = a.pos_val[a.cand_idx[(uint64_t)i * window + min(a.chosen[poly], window - 1)]];
+      if (poly < a.batch && i < degree) {
+        // (a draw that ran out of the evaluated nonces leaves its remaining indices unwritten; the chain reports that and the
+        //  host retries, but this kernel has been launched already: keep whatever it reads inside pos_val)
+        const uint32_t idx = a.cand_idx[(uint64_t)i * window + min(a.chosen[poly], window - 1)];
+        v = a.pos_val[min(idx, a.rows * (uint32_t)a.words_per_fill - 1u)];
+      }
       tile[ty][tx] = v;
     }
     __syncthreads();
