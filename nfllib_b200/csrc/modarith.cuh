@@ -139,6 +139,10 @@ static NFLGPU_DEVFN uint64_t csub_top(uint64_t x, uint64_t n2p) {
 #endif
 }
 static NFLGPU_DEVFN uint32_t csub_top(uint32_t x, uint32_t) { return x; }  // (32-bit words keep csub_lazy)
+// The same reduction written as a select (experiment build -DNFLGPU_LAZY64=2): five instructions like csub_lazy, carries in
+// freely allocated predicates, and the compare still independent of the add — for the kernels where the predicated form loses.
+static NFLGPU_DEVFN uint64_t csub_top_select(uint64_t x, uint64_t n2p) { return (int64_t)x < 0 ? x + n2p : x; }
+static NFLGPU_DEVFN uint32_t csub_top_select(uint32_t x, uint32_t) { return x; }
 // a - b + c as one three-input add with two carries (IADD3 + IADD3.X); written in PTX so that the front end
 // does not reassociate the sum into two separate 64-bit additions
 static NFLGPU_DEVFN uint64_t subadd(uint64_t a, uint64_t b, uint64_t c) {

@@ -58,9 +58,11 @@ template <int LB, int LOGN> struct NttCfg {
   // sub-partition) lose 10-13 % with it -- ptxas routes every predicated carry through one predicate register, which
   // serialises the sixteen conditional subtracts of a stage -- so they keep the [0, 4p) form.
 #if defined(NFLGPU_LAZY64)
-  static constexpr bool TOP = NFLGPU_LAZY64 != 0 && WB == 64;
+  static constexpr bool TOP = NFLGPU_LAZY64 != 0 && WB == 64;                       // experiment builds: 0 off, 1 everywhere,
+  static constexpr bool TOP_SELECT = NFLGPU_LAZY64 == 2 && WB == 64 && e > 4;         // 2 = select form on the 32-coefficient kernels
 #else
   static constexpr bool TOP = WB == 64 && e <= 4;
+  static constexpr bool TOP_SELECT = false;
 #endif
   static constexpr int NP = plan_npass(n, WB);
   static constexpr int SPLIT = plan_split(n, WB);        // leading passes run as global-memory kernels (0 unless N is huge)
@@ -191,7 +193,7 @@ template <class C, int PASS> NFLGPU_DEVFN void fwd_pass(typename C::Word (&x)[C:
       const int eidx = (1 << q) - 1 + (k >> (e - q));
       const typename C::TW t = tw[eidx * G];
       Word X = x[k];
-      if (!(PASS == 0 && q == 0)) X = C::TOP ? csub_top(X, n2p) : csub_lazy(X, twop);  // first stage sees canonical input
+      if (!(PASS == 0 && q == 0)) X = C::TOP ? (C::TOP_SELECT ? csub_top_select(X, n2p) : csub_top(X, n2p)) : csub_lazy(X, twop);  // first stage sees canonical input
       const Word T = A::mul_shoup_lazy(x[k | (1 << bit)], A::tw_w(t), A::tw_ws(t), np);
       x[k] = X + T;
       x[k | (1 << bit)] = C::TOP ? subadd(X, T, twop) : X - T + twop;
