@@ -168,8 +168,18 @@ int run_ntt(nflgpu_ctx *ctx, int mode, void *dst, const void *src, size_t batch,
     std::lock_guard<std::mutex> lock(ctx->sched_mu);
     uint32_t *&set = ctx->sched_by_stream[stream];
     if (!set) {
-      CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&set), (ctx->nmoduli + 1) * sizeof(uint32_t)));
-      CUDA_TRY(cudaMemset(set, 0, (ctx->nmoduli + 1) * sizeof(uint32_t)));
+      // zeroed on the launch stream itself: a cudaMemset on the legacy default stream is not ordered with a
+      // non-blocking stream, and the first kernel would read the counters of a fresh allocation
+      uint32_t *fresh = nullptr;
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void **>(&fresh), (ctx->nmoduli + 1) * sizeof(uint32_t)));
+      cudaError_t e = cudaMemsetAsync(fresh, 0, (ctx->nmoduli + 1) * sizeof(uint32_t), (cudaStream_t)stream);
+      if (e != cudaSuccess) {
+        cudaFree(fresh);
+        ctx->sched_by_stream.erase(stream);
+        set_error(std::string("scheduler counters: ") + cudaGetErrorName(e));
+        return NFLGPU_ERR_CUDA;
+      }
+      set = fresh;
     }
     l.sched = set;
   }

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(GAUSS_WALK_THREADS) gauss_walk_kernel(const Ga
   uint32_t *__restrict__ out = a.cand_idx + c;
   uint32_t n = c, pos = 0, calls = 1;
   const unsigned char *row = gsm + (size_t)threadIdx.x * stride;  // row of nonce n while it is staged
-  bool in_smem = true;
+  bool in_smem = threadIdx.x < staged;  // large degrees stage fewer rows than the CTA has candidates: the others read global memory
   for (uint32_t k = 0; k < degree; ++k) {
     if (n >= rows) { calls = 0x40000000u; break; }  // ran past the evaluated nonces: the chain treats it as "window too small"
     out[(uint64_t)k * window] = n * words + pos;      // index into pos_val (rows * words < 2^32: the caller's chunking bounds it)

@@ -181,3 +181,22 @@ def test_device_gaussian_next_to_the_live_reference():
         assert np.array_equal(got, want)
     g.close()
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,N,M,batch", [(64, 8192, 2, 48), (64, 32768, 1, 40), (32, 16384, 2, 40), (64, 4096, 3, 70)])
+def test_device_gaussian_large_degrees_stage_fewer_rows_than_candidates(bits, N, M, batch):
+    """Degrees >= 8192 have a consumed-words pitch above 6400 bytes, so a walk CTA stages fewer than 32 rows in shared memory and
+    the remaining candidates follow their chain in global memory (round-1 ADVICE: those threads read past the staged rows)."""
+    z, meta = fixture()
+    m = meta["demo_u64"]
+    t = table_of(z, "demo_u64", m)
+    ctx = capi.Context(bits, N, M)
+    g = capi.Gaussian(ctx, in_bytes=m["in_bytes"], lu_depth=m["lu_depth"], barriers=t.barriers, rounded_center=m["rounded_center"])
+    key = bytes((11 * i + 5) & 0xFF for i in range(32))
+    want, calls = Oracle(bits, N, M).gaussian(batch, t, 1, key, 4242)
+    got, used = device_draws(ctx, g, batch, key, 4242, 1)
+    assert used == calls
+    assert np.array_equal(got, want)
+    g.close()
+    ctx.close()
