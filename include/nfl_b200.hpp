@@ -14,8 +14,10 @@
 // A single host-resident poly per call is PCIe-bound (hard part 5); throughput code should
 // use nfl::cuda::batch<poly> below, which keeps `count` polys resident in HBM between operations.
 //
-// Out of scope here: FastGaussianNoise::getNoise for free-standing arrays, GMP lifting, poly_p,
-// serialization (the byte layout is identical, so reference-serialized polys can be memcpy'd in).
+// Also here: poly_p (copy-on-write handle, poly_p.hpp), serialize_manually / deserialize_manually (poly.hpp:180-191; the byte
+// layout is identical, so reference-serialized polys load unchanged), the samplers behind poly::set(...), and the CRT lift
+// as batch::poly2words / words2poly (GMP types themselves stay out: the lift works on little-endian 64-bit words).
+// Out of scope: FastGaussianNoise::getNoise into free-standing arrays, cereal serialization.
 #ifndef NFL_B200_HPP
 #define NFL_B200_HPP
 
@@ -228,11 +230,20 @@ template <class T, size_t Degree> struct residue_backend {
   }
 };
 
-// RAII device buffer of `count` polys
+// RAII device buffer of `count` polys.  Temporaries of single-poly calls (pooled = true, the default) come from the
+// context's stream-ordered pool (nflgpu_scratch_alloc: a cached block, no cudaMalloc / cudaFree per leaf of an expression);
+// long-lived batches (nfl::cuda::batch) own a plain allocation that can also be exported to a peer process.
 template <class P> struct dev_buf {
-  void *p; size_t count;
-  explicit dev_buf(size_t n) : p(nullptr), count(n) { check(nflgpu_alloc(P::backend_type::get().ctx, n, &p), "nflgpu_alloc"); }
-  ~dev_buf() { if (p) nflgpu_free(P::backend_type::get().ctx, p); }
+  void *p; size_t count; bool pooled;
+  explicit dev_buf(size_t n, bool pooled_ = true) : p(nullptr), count(n), pooled(pooled_) {
+    if (pooled) check(nflgpu_scratch_alloc(P::backend_type::get().ctx, n, &p, nullptr), "nflgpu_scratch_alloc");
+    else check(nflgpu_alloc(P::backend_type::get().ctx, n, &p), "nflgpu_alloc");
+  }
+  ~dev_buf() {
+    if (!p) return;
+    if (pooled) nflgpu_scratch_free(P::backend_type::get().ctx, p, nullptr);
+    else nflgpu_free(P::backend_type::get().ctx, p);
+  }
   dev_buf(const dev_buf &) = delete;
   dev_buf &operator=(const dev_buf &) = delete;
 };
@@ -803,10 +814,22 @@ namespace cuda {
 template <class P> class batch {
   detail::dev_buf<P> buf_;
   static nflgpu_ctx *ctx() { return P::backend_type::get().ctx; }
+  static std::vector<bool> compare(batch const &a, batch const &b, bool want_equal) {
+    if (a.size() != b.size()) throw std::runtime_error("nfl::cuda::batch: size mismatch");
+    // the flags travel in a (pooled) buffer of whole polys: ceil(count / sizeof(P)) polys hold count bytes
+    detail::dev_buf<P> flags((a.size() + sizeof(P) - 1) / sizeof(P));
+    uint8_t *f = static_cast<uint8_t *>(flags.p);
+    detail::check(want_equal ? nflgpu_any_eq(ctx(), f, a.buf_.p, b.buf_.p, a.size(), nullptr)
+                             : nflgpu_any_neq(ctx(), f, a.buf_.p, b.buf_.p, a.size(), nullptr), "nflgpu_any_eq");
+    std::vector<uint8_t> host(flags.count * sizeof(P));
+    detail::check(nflgpu_download(ctx(), host.data(), flags.p, flags.count, nullptr), "nflgpu_download");
+    sync();
+    return std::vector<bool>(host.begin(), host.begin() + a.size());
+  }
 
 public:
-  explicit batch(size_t count) : buf_(count) {}
-  batch(P const *host, size_t count) : buf_(count) { upload(host); }
+  explicit batch(size_t count) : buf_(count, false) {}
+  batch(P const *host, size_t count) : buf_(count, false) { upload(host); }
   size_t size() const { return buf_.count; }
   void *device_ptr() { return buf_.p; }
   const void *device_ptr() const { return buf_.p; }
@@ -871,6 +894,10 @@ public:
     }
     detail::check(nflgpu_eval(ctx(), buf_.p, ptrs.data(), ptrs.size(), program.data(), program.size(), buf_.count, nullptr), "nflgpu_eval");
   }
+  // operator== / operator!= of every polynomial pair, the reference's ANY-coefficient semantics (ops.hpp:81-117), compared
+  // in HBM: result[i] = (a[i] == b[i]) as the reference's expr::operator bool would give it
+  static std::vector<bool> any_equal(batch const &a, batch const &b) { return compare(a, b, true); }
+  static std::vector<bool> any_different(batch const &a, batch const &b) { return compare(a, b, false); }
   void assign_muladd(batch const &a, batch const &b, batch const &c) {  // *this = a + b * c
     detail::check(nflgpu_muladd(ctx(), buf_.p, a.buf_.p, b.buf_.p, c.buf_.p, buf_.count, nullptr), "nflgpu_muladd");
   }

@@ -82,6 +82,12 @@ int nflgpu_params_limits(int limb_bits, uint64_t *kMaxPolyDegree, uint64_t *kMax
 size_t nflgpu_batch_bytes(const nflgpu_ctx *ctx, size_t batch);
 int nflgpu_alloc(nflgpu_ctx *ctx, size_t batch, void **dptr);
 int nflgpu_free(nflgpu_ctx *ctx, void *dptr);
+/* Stream-ordered temporaries from a pool owned by the context (cudaMallocFromPoolAsync / cudaFreeAsync): what the C++ header
+ * uses for the operands of a single-poly expression instead of a cudaMalloc / cudaFree pair per leaf.  Freed blocks stay
+ * cached in the pool; nflgpu_ctx_trim returns them to the driver (it synchronises the device), nflgpu_ctx_destroy drops the pool. */
+int nflgpu_scratch_alloc(nflgpu_ctx *ctx, size_t batch, void **dptr, void *stream);
+int nflgpu_scratch_free(nflgpu_ctx *ctx, void *dptr, void *stream);
+int nflgpu_ctx_trim(nflgpu_ctx *ctx);
 int nflgpu_upload(nflgpu_ctx *ctx, void *dst_dev, const void *src_host, size_t batch, void *stream);
 int nflgpu_download(nflgpu_ctx *ctx, void *dst_host, const void *src_dev, size_t batch, void *stream);
 int nflgpu_sync(nflgpu_ctx *ctx, void *stream);
@@ -123,6 +129,12 @@ int nflgpu_muladd(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, cons
 /* a + shoup(b*c, cprime) = ops::muladd_shoup (opt/ops.hpp:56-78), canonical result. */
 int nflgpu_muladd_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, const void *c,
                         const void *cprime, size_t batch, void *stream);
+
+/* operator== / operator!= on device-resident batches, with the reference's semantics (expr::operator bool over
+ * ops::eqmod / ops::neqmod, ops.hpp:81-117): flags[b] = 1 iff ANY coefficient of a[b] equals (any_eq) / differs from (any_neq)
+ * the same coefficient of b[b], else 0.  `flags` is uint8_t[batch] in device memory. */
+int nflgpu_any_eq(nflgpu_ctx *ctx, uint8_t *flags, const void *a, const void *b, size_t batch, void *stream);
+int nflgpu_any_neq(nflgpu_ctx *ctx, uint8_t *flags, const void *a, const void *b, size_t batch, void *stream);
 
 /* Fused evaluation of an ARBITRARY expression tree in one pass over memory — what the reference's expression
  * templates do (ops::expr ops.hpp:52-97, _make_op rewrite ops.hpp:249-277, evaluator core.hpp:24-37): `c = a + b*d - e`
@@ -212,6 +224,24 @@ int nflgpu_gaussian_sample(nflgpu_ctx *ctx, const nflgpu_gaussian *g, void *dst,
 int nflgpu_lift_words(nflgpu_ctx *ctx, size_t *words_per_coefficient);
 int nflgpu_poly2mpz(nflgpu_ctx *ctx, uint64_t *dst_words, const void *src_polys, size_t batch, void *stream);
 int nflgpu_mpz2poly(nflgpu_ctx *ctx, void *dst_polys, const uint64_t *src_words, size_t batch, void *stream);
+
+/* ---- residues sharded over GPUs: gathering the full RNS vector ----------------------- *
+ * The path itself needs no exchange: a context created with first_modulus = r0 and nmoduli = k transforms the slab
+ * limb[batch][k][degree] of residues r0 .. r0+k-1 on its own device.  Only a consumer that needs every residue of a
+ * polynomial on one device (the CRT lift, gmp.hpp:183-209) gathers: nflgpu_gather_residues writes `nslabs` slabs
+ * limb[batch][nresidues[s]][degree] into dst_full = limb[batch][nmoduli][degree] of the FULL context `ctx` at residue offset
+ * first_residue[s], one strided copy-engine transfer per slab (peer memory is pulled over NVLink / NVSwitch).
+ * A slab may live on this device or on a peer: one process per GPU exports its slab with nflgpu_ipc_export (a CUDA IPC
+ * handle, 64 opaque bytes to ship through any channel — MPI, torch.distributed, a pipe), the gathering process maps it with
+ * nflgpu_ipc_open and passes the mapped pointer.  `dptr` must be the start of an allocation made by nflgpu_alloc.
+ * Ordering across processes (the slab is complete before it is read, not overwritten while it is read) is the caller's:
+ * synchronise the producing stream and pass a barrier, as with any peer-memory transfer. */
+typedef struct { unsigned char bytes[64]; } nflgpu_ipc_handle;
+int nflgpu_ipc_export(nflgpu_ctx *ctx, const void *dptr, nflgpu_ipc_handle *out);
+int nflgpu_ipc_open(nflgpu_ctx *ctx, const nflgpu_ipc_handle *handle, void **peer_ptr);
+int nflgpu_ipc_close(nflgpu_ctx *ctx, void *peer_ptr);
+int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *slabs, const size_t *first_residue,
+                           const size_t *nresidues, size_t nslabs, size_t batch, void *stream);
 
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked

@@ -72,6 +72,15 @@ def lib():
         L.nflgpu_poly2mpz.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_mpz2poly.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_eval.argtypes = [vp, vp, ctypes.POINTER(vp), sz, ctypes.c_char_p, sz, sz, vp]
+        L.nflgpu_scratch_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), vp]
+        L.nflgpu_scratch_free.argtypes = [vp, vp, vp]
+        L.nflgpu_ctx_trim.argtypes = [vp]
+        L.nflgpu_any_eq.argtypes = [vp, vp, vp, vp, sz, vp]
+        L.nflgpu_any_neq.argtypes = [vp, vp, vp, vp, sz, vp]
+        L.nflgpu_ipc_export.argtypes = [vp, vp, vp]
+        L.nflgpu_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
+        L.nflgpu_ipc_close.argtypes = [vp, vp]
+        L.nflgpu_gather_residues.argtypes = [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, sz, vp]
         _lib = L
     return _lib
 
@@ -260,6 +269,48 @@ class Context:
 
     def polymul(self, dst, a, b, batch, stream=0):
         _check(lib().nflgpu_polymul(self.h, dst, a, b, batch, stream))
+
+    def scratch_alloc(self, batch, stream=0):
+        p = ctypes.c_void_p()
+        _check(lib().nflgpu_scratch_alloc(self.h, batch, ctypes.byref(p), stream))
+        return p.value
+
+    def scratch_free(self, dptr, stream=0):
+        _check(lib().nflgpu_scratch_free(self.h, dptr, stream))
+
+    def trim(self):
+        _check(lib().nflgpu_ctx_trim(self.h))
+
+    def any_eq(self, flags, a, b, batch, stream=0):
+        """nflgpu_any_eq: flags[i] (uint8, device) = any coefficient of a[i] equals that of b[i] (ops.hpp:81-117)."""
+        _check(lib().nflgpu_any_eq(self.h, flags, a, b, batch, stream))
+
+    def any_neq(self, flags, a, b, batch, stream=0):
+        _check(lib().nflgpu_any_neq(self.h, flags, a, b, batch, stream))
+
+    # ---- residues sharded over devices ----
+    def ipc_export(self, dptr):
+        """64 opaque bytes naming the allocation `dptr` (from alloc()) for another process on this node."""
+        h = ctypes.create_string_buffer(64)
+        _check(lib().nflgpu_ipc_export(self.h, dptr, h))
+        return h.raw
+
+    def ipc_open(self, handle):
+        h = ctypes.create_string_buffer(bytes(handle), 64)
+        p = ctypes.c_void_p()
+        _check(lib().nflgpu_ipc_open(self.h, h, ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, peer_ptr):
+        _check(lib().nflgpu_ipc_close(self.h, peer_ptr))
+
+    def gather_residues(self, dst_full, slabs, batch, stream=0):
+        """nflgpu_gather_residues on this (full) context: slabs = [(device pointer, first_residue, nresidues), ...]."""
+        n = len(slabs)
+        ptrs = (ctypes.c_void_p * n)(*[s[0] for s in slabs])
+        first = (ctypes.c_size_t * n)(*[s[1] for s in slabs])
+        cnt = (ctypes.c_size_t * n)(*[s[2] for s in slabs])
+        _check(lib().nflgpu_gather_residues(self.h, dst_full, ptrs, first, cnt, n, batch, stream))
 
     # ---- host-buffer call (numpy in, numpy out): H2D + kernel(s) + D2H inside the library ----
     def host_op(self, op, a, b=None, c=None, out=None):

@@ -79,6 +79,9 @@ struct nflgpu_ctx {
   int lift_words = 0;
   uint64_t *d_lift = nullptr;  // [inv | c64 | qhat (M*W) | q (W)]
   std::atomic<uint64_t> launches{0};
+  // stream-ordered scratch (nflgpu_polymul temporaries, sampler scratch, nflgpu_scratch_alloc): a pool owned by the context,
+  // destroyed with it, so that cached blocks never outlive the context or touch the application's default pool
+  cudaMemPool_t pool = nullptr;
   // dynamic unit scheduling of the NTT kernels (ntt_engine.cuh UnitWalk): one set of nmoduli + 1 device counters per
   // stream, created the first time the stream is seen.  Launches on one stream are ordered and every launch leaves its set
   // zeroed, so a set is never shared by two running kernels.  (A CUDA graph must be replayed on the stream it was captured
@@ -287,15 +290,20 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
   if (!g.ok || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; set_error("cannot query CUDA device"); return NFLGPU_ERR_CUDA; }
   ctx->num_sms = prop.multiProcessorCount;
 
-  // nflgpu_polymul takes its scratch from the device's stream-ordered pool; keep freed blocks cached instead of
-  // returning them to the driver at every synchronisation (default threshold 0 made a 768 MiB scratch cost 15 ms per call)
+  // scratch comes from a pool of the context's own; freed blocks stay cached in it (with the default threshold 0 a
+  // 768 MiB polymul scratch cost 15 ms per call) and are returned to the driver by nflgpu_ctx_trim / nflgpu_ctx_destroy
   {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    cudaMemPoolProps props;
+    std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&ctx->pool, &props) != cudaSuccess) {
+      cudaGetLastError(); delete ctx; set_error("cannot create the context's memory pool"); return NFLGPU_ERR_CUDA;
     }
-    cudaGetLastError();
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   ctx->roots = rts;
   ctx->kmax = lim.kMaxPolyDegree;
@@ -341,6 +349,7 @@ int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
   }
   cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
   for (auto &kv : ctx->sched_by_stream) cudaFree(kv.second);
+  if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
   delete ctx;
   return NFLGPU_OK;
 }
@@ -376,6 +385,32 @@ int nflgpu_free(nflgpu_ctx *ctx, void *dptr) {
   if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
   DeviceGuard g(ctx->device);
   CUDA_TRY(cudaFree(dptr));
+  return NFLGPU_OK;
+}
+
+int nflgpu_scratch_alloc(nflgpu_ctx *ctx, size_t batch, void **dptr, void *stream) {
+  if (!ctx || !dptr) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  const size_t bytes = nflgpu_batch_bytes(ctx, batch);
+  if (cudaMallocFromPoolAsync(dptr, bytes ? bytes : 16, ctx->pool, (cudaStream_t)stream) != cudaSuccess) {
+    cudaGetLastError(); set_error("cudaMallocFromPoolAsync failed"); return NFLGPU_ERR_ALLOC;
+  }
+  return NFLGPU_OK;
+}
+
+int nflgpu_scratch_free(nflgpu_ctx *ctx, void *dptr, void *stream) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  if (!dptr) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaFreeAsync(dptr, (cudaStream_t)stream));
+  return NFLGPU_OK;
+}
+
+int nflgpu_ctx_trim(nflgpu_ctx *ctx) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemPoolTrimTo(ctx->pool, 0));
   return NFLGPU_OK;
 }
 
@@ -433,6 +468,26 @@ int nflgpu_muladd_shoup(nflgpu_ctx *ctx, void *dst, const void *a, const void *b
   return run_pw(ctx, PW_MULADD_SHOUP, 4, dst, a, b, c, cprime, batch, stream);
 }
 
+static int run_compare(nflgpu_ctx *ctx, bool want_equal, uint8_t *flags, const void *a, const void *b, size_t batch, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, a, "a")) || (rc = check_buf(ctx, b, "b"))) return rc;
+  if (!flags) { set_error("null flags buffer"); return NFLGPU_ERR_ARG; }
+  if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  CUDA_TRY(launch_compare(ctx->limb_bits, want_equal, a, b, flags, (uint32_t)batch, ctx->nmoduli * ctx->degree * ctx->limb_bytes, ctx->num_sms,
+                          (cudaStream_t)stream));
+  ctx->launches++;
+  return NFLGPU_OK;
+}
+int nflgpu_any_eq(nflgpu_ctx *ctx, uint8_t *flags, const void *a, const void *b, size_t batch, void *stream) {
+  return run_compare(ctx, true, flags, a, b, batch, stream);
+}
+int nflgpu_any_neq(nflgpu_ctx *ctx, uint8_t *flags, const void *a, const void *b, size_t batch, void *stream) {
+  return run_compare(ctx, false, flags, a, b, batch, stream);
+}
+
 int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t noperands, const uint8_t *program, size_t ntokens,
                 size_t batch, void *stream) {
   int rc;
@@ -465,10 +520,29 @@ int nflgpu_eval(nflgpu_ctx *ctx, void *dst, const void *const *operands, size_t 
   EvArgs a;
   std::memset(&a, 0, sizeof(a));
   a.dst = dst;
-  for (size_t i = 0; i < noperands; ++i) a.operands[i] = operands[i];
   a.moduli = ctx->d_moduli64; a.consts = ctx->d_consts;
   a.nmoduli = (uint32_t)ctx->nmoduli; a.degree = (uint32_t)ctx->degree; a.log2_degree = (uint32_t)ctx->log2_degree;
   a.batch = (uint32_t)batch; a.ntokens = (uint32_t)ntokens;
+  // Small trees have a kernel compiled for their program (eval_static.cu): canonical form = every leaf occurrence becomes a
+  // leaf of its own, numbered in order of appearance (an operand used twice is simply passed twice)
+  if (ntokens <= 7 && !std::getenv("NFLGPU_EVAL_INTERPRET")) {
+    uint64_t key = 0;
+    size_t nleaves = 0;
+    for (size_t t = 0; t < ntokens; ++t) {
+      uint8_t tok = program[t];
+      if (tok < EV_MAX_OPERANDS) { a.operands[nleaves] = operands[tok]; tok = (uint8_t)nleaves++; }
+      a.program[t] = tok;
+      key |= (uint64_t)(tok + 1) << (8 * t);
+    }
+    cudaError_t e = cudaSuccess;
+    if (launch_eval_static(ctx->limb_bits, key, a, ctx->num_sms, (cudaStream_t)stream, &e)) {
+      CUDA_TRY(e);
+      ctx->launches++;
+      return NFLGPU_OK;
+    }
+    std::memset(a.operands, 0, sizeof(a.operands));
+  }
+  for (size_t i = 0; i < noperands; ++i) a.operands[i] = operands[i];
   std::memcpy(a.program, program, ntokens);
   CUDA_TRY(launch_eval(ctx->limb_bits, a, ctx->num_sms, (cudaStream_t)stream));
   ctx->launches++;
@@ -576,7 +650,7 @@ static int run_sampler(nflgpu_ctx *ctx, int kind, void *dst, size_t batch, const
   a.nmoduli = (uint32_t)ctx->nmoduli; a.log2_degree = (uint32_t)ctx->log2_degree; a.limb_bits = (uint32_t)ctx->limb_bits;
   a.batch = (uint32_t)batch;
   a.param0 = p0; a.param1 = p1; a.param2 = p2;
-  CUDA_TRY(launch_sampler(kind, a, ctx->num_sms, (cudaStream_t)stream));
+  CUDA_TRY(launch_sampler(kind, a, ctx->num_sms, (cudaStream_t)stream, ctx->pool));
   ctx->launches++;
   return NFLGPU_OK;
 }
@@ -745,7 +819,7 @@ int nflgpu_gaussian_sample(nflgpu_ctx *ctx, const nflgpu_gaussian *g, void *dst,
     const size_t small_bytes = (((size_t)a.window * 4 + nb * 4) + 15) & ~(size_t)15, pitch = (words + 15) & ~(size_t)15;
     const size_t bytes = 16 + val_bytes + idx_bytes + small_bytes + (size_t)a.rows * pitch;
     unsigned char *scratch = nullptr;
-    CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&scratch), bytes, s));
+    CUDA_TRY(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), bytes, ctx->pool, s));
     a.result = reinterpret_cast<uint64_t *>(scratch);
     a.pos_val = reinterpret_cast<int32_t *>(scratch + 16);
     a.cand_idx = reinterpret_cast<uint32_t *>(scratch + 16 + val_bytes);
@@ -783,7 +857,7 @@ int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, siz
   cudaStream_t s = (cudaStream_t)stream;
   void *tmp = nullptr;
   const size_t bytes = nflgpu_batch_bytes(ctx, batch);
-  CUDA_TRY(cudaMallocAsync(&tmp, bytes, s));
+  CUDA_TRY(cudaMallocFromPoolAsync(&tmp, bytes, ctx->pool, s));
   // three launches: tmp = ntt(a);  dst = ntt(b) * tmp (product fused into the forward kernel's copy-out);  dst = intt(dst)
   if ((rc = run_ntt(ctx, 0, tmp, a, batch, stream)) || (rc = run_ntt(ctx, 2, dst, b, batch, stream, tmp)) ||
       (rc = run_ntt(ctx, 1, dst, dst, batch, stream))) {
@@ -791,6 +865,59 @@ int nflgpu_polymul(nflgpu_ctx *ctx, void *dst, const void *a, const void *b, siz
     return rc;
   }
   CUDA_TRY(cudaFreeAsync(tmp, s));
+  return NFLGPU_OK;
+}
+
+// ---- residues sharded over devices: peer-memory gather -----------------------------------------
+
+int nflgpu_ipc_export(nflgpu_ctx *ctx, const void *dptr, nflgpu_ipc_handle *out) {
+  if (!ctx || !dptr || !out) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(out->bytes), "CUDA IPC handle does not fit nflgpu_ipc_handle");
+  DeviceGuard g(ctx->device);
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+  std::memset(out->bytes, 0, sizeof(out->bytes));
+  std::memcpy(out->bytes, &h, sizeof(h));
+  return NFLGPU_OK;
+}
+
+int nflgpu_ipc_open(nflgpu_ctx *ctx, const nflgpu_ipc_handle *handle, void **peer_ptr) {
+  if (!ctx || !handle || !peer_ptr) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle->bytes, sizeof(h));
+  CUDA_TRY(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return NFLGPU_OK;
+}
+
+int nflgpu_ipc_close(nflgpu_ctx *ctx, void *peer_ptr) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  if (!peer_ptr) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaIpcCloseMemHandle(peer_ptr));
+  return NFLGPU_OK;
+}
+
+int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *slabs, const size_t *first_residue, const size_t *nresidues,
+                           size_t nslabs, size_t batch, void *stream) {
+  int rc;
+  if ((rc = check_buf(ctx, dst_full, "dst_full"))) return rc;
+  if (!slabs || !first_residue || !nresidues || nslabs == 0) { set_error("nflgpu_gather_residues: null argument"); return NFLGPU_ERR_ARG; }
+  const size_t row = ctx->degree * ctx->limb_bytes, full_pitch = ctx->nmoduli * row;
+  for (size_t k = 0; k < nslabs; ++k) {
+    if ((rc = check_buf(ctx, slabs[k], "slab"))) return rc;
+    if (nresidues[k] == 0 || first_residue[k] + nresidues[k] > ctx->nmoduli) { set_error("nflgpu_gather_residues: residue range outside the context"); return NFLGPU_ERR_ARG; }
+  }
+  if (batch == 0) return NFLGPU_OK;
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  // one strided DMA per slab: `batch` rows of nres*N limbs, written where they belong in [batch][M][N] (no padded slabs, no
+  // second interleave pass); for a slab in a peer device's memory the copy engine pulls it over NVLink
+  for (size_t k = 0; k < nslabs; ++k) {
+    const size_t width = nresidues[k] * row;
+    CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(dst_full) + first_residue[k] * row, full_pitch, slabs[k], width, width, batch,
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
   return NFLGPU_OK;
 }
 
@@ -862,16 +989,28 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   if (chunk == 0) chunk = 1;
   if (chunk > batch) chunk = batch;
   if (ctx->stage_polys < chunk) {  // staging buffers only ever grow (capacity = largest chunk seen so far)
+    ctx->stage_polys = 0;  // a failure below leaves "no staging buffers": the next call allocates all of them again
     for (auto &s : ctx->stage) {
       if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
       for (int i = 0; i < 4; ++i) {
-        if (s.dev[i]) { CUDA_TRY(cudaFree(s.dev[i])); s.dev[i] = nullptr; }
-        if (s.pin[i]) { CUDA_TRY(cudaFreeHost(s.pin[i])); s.pin[i] = nullptr; }
+        if (s.dev[i]) { void *old = s.dev[i]; s.dev[i] = nullptr; CUDA_TRY(cudaFree(old)); }
+        if (s.pin[i]) { void *old = s.pin[i]; s.pin[i] = nullptr; CUDA_TRY(cudaFreeHost(old)); }
         CUDA_TRY(cudaMalloc(&s.dev[i], chunk * poly_bytes));
       }
     }
     ctx->stage_polys = chunk;
   }
+  // any failure inside the pipeline drains every stage stream before returning: asynchronous copies still target the
+  // caller's buffers and the pinned staging
+#define PIPE_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      set_error(std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
+      rc = NFLGPU_ERR_CUDA;                                                                              \
+      goto drain;                                                                                        \
+    }                                                                                                    \
+  } while (0)
   bool pinned[4] = {is_pinned(a_host), nin >= 2 && is_pinned(b_host), nin >= 3 && is_pinned(c_host), is_pinned(dst_host)};
   constexpr int NS = nflgpu_ctx::kStages;
   struct Pending { size_t first, count; bool active; } pend[NS] = {};
@@ -881,7 +1020,7 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   for (int k = 0; done < batch || any_pending(); k = (k + 1) % NS) {
     HostStage &s = ctx->stage[k];
     if (pend[k].active) {  // retire the chunk that used this stage kStages steps ago
-      CUDA_TRY(cudaStreamSynchronize(s.stream));
+      PIPE_TRY(cudaStreamSynchronize(s.stream));
       if (!pinned[3]) std::memcpy(static_cast<char *>(dst_host) + pend[k].first * poly_bytes, s.pin[3], pend[k].count * poly_bytes);
       pend[k].active = false;
     }
@@ -890,11 +1029,11 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
     for (int i = 0; i < nin; ++i) {
       const char *src = static_cast<const char *>(in[i]) + done * poly_bytes;
       if (!pinned[i]) {
-        if (!s.pin[i]) CUDA_TRY(cudaHostAlloc(&s.pin[i], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
+        if (!s.pin[i]) PIPE_TRY(cudaHostAlloc(&s.pin[i], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
         std::memcpy(s.pin[i], src, cnt * poly_bytes);
         src = static_cast<const char *>(s.pin[i]);
       }
-      CUDA_TRY(cudaMemcpyAsync(s.dev[i], src, cnt * poly_bytes, cudaMemcpyHostToDevice, s.stream));
+      PIPE_TRY(cudaMemcpyAsync(s.dev[i], src, cnt * poly_bytes, cudaMemcpyHostToDevice, s.stream));
     }
     void *st = s.stream;
     switch (op) {
@@ -910,16 +1049,18 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
       case 10: rc = nflgpu_ntt_raw_fwd(ctx, s.dev[3], s.dev[0], cnt, st); break;
       case 11: rc = nflgpu_ntt_raw_inv(ctx, s.dev[3], s.dev[0], cnt, st); break;
     }
-    if (rc != NFLGPU_OK) break;
+    if (rc != NFLGPU_OK) goto drain;
     char *out = static_cast<char *>(dst_host) + done * poly_bytes;
     if (!pinned[3]) {
-      if (!s.pin[3]) CUDA_TRY(cudaHostAlloc(&s.pin[3], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
+      if (!s.pin[3]) PIPE_TRY(cudaHostAlloc(&s.pin[3], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
       out = static_cast<char *>(s.pin[3]);
     }
-    CUDA_TRY(cudaMemcpyAsync(out, s.dev[3], cnt * poly_bytes, cudaMemcpyDeviceToHost, s.stream));
+    PIPE_TRY(cudaMemcpyAsync(out, s.dev[3], cnt * poly_bytes, cudaMemcpyDeviceToHost, s.stream));
     pend[k] = {done, cnt, true};
     done += cnt;
   }
+drain:
+#undef PIPE_TRY
   if (rc != NFLGPU_OK) for (auto &s : ctx->stage) if (s.stream) cudaStreamSynchronize(s.stream);
   return rc;
 }

@@ -9,41 +9,11 @@
 #include "pointwise.h"
 #include "modarith.cuh"
 #include "modmul.cuh"
+#include "vecio.cuh"
 
 namespace nflgpu {
 
 // (the functors themselves are in modmul.cuh: Functor<LB, OP>::apply, shared with the host simulation of the CPU suite)
-
-template <int LB> struct VecIO;
-template <> struct VecIO<64> {
-  static __device__ __forceinline__ void load(uint64_t (&w)[2], const uint64_t *g) {
-    const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(g));
-    w[0] = t.x; w[1] = t.y;
-  }
-  static __device__ __forceinline__ void store(uint64_t *g, const uint64_t (&w)[2]) {
-    *reinterpret_cast<ulonglong2 *>(g) = make_ulonglong2(w[0], w[1]);
-  }
-};
-template <> struct VecIO<32> {
-  static __device__ __forceinline__ void load(uint32_t (&w)[4], const uint32_t *g) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(g));
-    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
-  }
-  static __device__ __forceinline__ void store(uint32_t *g, const uint32_t (&w)[4]) {
-    *reinterpret_cast<uint4 *>(g) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-template <> struct VecIO<16> {
-  static __device__ __forceinline__ void load(uint32_t (&w)[8], const uint16_t *g) {
-    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(g));
-    const uint32_t v[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { w[2 * i] = v[i] & 0xffffu; w[2 * i + 1] = v[i] >> 16; }
-  }
-  static __device__ __forceinline__ void store(uint16_t *g, const uint32_t (&w)[8]) {
-    *reinterpret_cast<uint4 *>(g) = make_uint4(w[0] | (w[1] << 16), w[2] | (w[3] << 16), w[4] | (w[5] << 16), w[6] | (w[7] << 16));
-  }
-};
 
 template <int LB, int OP, int NIN>
 __global__ void __launch_bounds__(256) pointwise_kernel(const PwArgs a) {
@@ -170,6 +140,56 @@ cudaError_t launch_eval(int limb_bits, const EvArgs &a, int num_sms, cudaStream_
     case 16: return launch_eval_limb<16>(a, num_sms, stream);
   }
   return cudaErrorInvalidValue;
+}
+
+// ---- ==  /  != on device-resident batches --------------------------------------------------------------------------
+// expr::operator bool over eqmod / neqmod (ops.hpp:81-117): `a == b` is true iff ANY coefficient is equal, `a != b` iff ANY
+// coefficient differs.  One CTA per polynomial pair walks the M*N limbs as 16-byte vectors; flags[b] = 1 when the
+// predicate holds for polynomial b.  Reads each operand once: HBM-bound, 2*N*M*sizeof(T) bytes per polynomial.
+template <int LB, bool WANT_EQUAL>
+__global__ void __launch_bounds__(256) compare_kernel(const void *pa, const void *pb, uint8_t *flags, uint32_t batch, uint32_t vec_per_poly) {
+  const uint4 *a = reinterpret_cast<const uint4 *>(pa), *b = reinterpret_cast<const uint4 *>(pb);
+  for (uint32_t poly = blockIdx.x; poly < batch; poly += gridDim.x) {
+    const size_t base = (size_t)poly * vec_per_poly;
+    int hit = 0;
+    for (uint32_t v = threadIdx.x; v < vec_per_poly; v += blockDim.x) {
+      const uint4 x = __ldg(a + base + v), y = __ldg(b + base + v);
+      const uint32_t d[4] = {x.x ^ y.x, x.y ^ y.y, x.z ^ y.z, x.w ^ y.w};
+      if (LB == 64) {
+        const bool e0 = (d[0] | d[1]) == 0, e1 = (d[2] | d[3]) == 0;
+        hit |= WANT_EQUAL ? (e0 || e1) : (!e0 || !e1);
+      } else if (LB == 32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) hit |= WANT_EQUAL ? d[i] == 0 : d[i] != 0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool e0 = (d[i] & 0xffffu) == 0, e1 = (d[i] >> 16) == 0;
+          hit |= WANT_EQUAL ? (e0 || e1) : (!e0 || !e1);
+        }
+      }
+    }
+    hit = __syncthreads_or(hit);
+    if (threadIdx.x == 0) flags[poly] = hit ? 1 : 0;
+  }
+}
+
+cudaError_t launch_compare(int limb_bits, bool want_equal, const void *a, const void *b, uint8_t *flags, uint32_t batch, uint64_t poly_bytes,
+                           int num_sms, cudaStream_t stream) {
+  if (batch == 0) return cudaSuccess;
+  const uint32_t vec = (uint32_t)(poly_bytes / 16);
+  const unsigned grid = batch < (unsigned)num_sms * 8 ? batch : (unsigned)num_sms * 8;
+#define NFLGPU_CMP(LB) \
+  if (want_equal) compare_kernel<LB, true><<<grid, 256, 0, stream>>>(a, b, flags, batch, vec); \
+  else compare_kernel<LB, false><<<grid, 256, 0, stream>>>(a, b, flags, batch, vec); break;
+  switch (limb_bits) {
+    case 64: NFLGPU_CMP(64)
+    case 32: NFLGPU_CMP(32)
+    case 16: NFLGPU_CMP(16)
+    default: return cudaErrorInvalidValue;
+  }
+#undef NFLGPU_CMP
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pointwise(int limb_bits, int op, const PwArgs &a, int num_sms, cudaStream_t stream) {

@@ -397,12 +397,12 @@ cudaError_t launch_gaussian(GaussArgs a, int device, int num_sms, cudaStream_t s
   return cudaGetLastError();
 }
 
-cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream) {
+cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream, cudaMemPool_t pool) {
   if (a.batch == 0) return cudaSuccess;
   const uint64_t degree = 1ull << a.log2_degree, hwt = a.param0;
   const size_t hit_bytes = (size_t)a.batch * hwt * 4, bm_bytes = (size_t)a.batch * ((degree + 31) / 32) * 4;
   unsigned char *scratch = nullptr;
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&scratch), hit_bytes + bm_bytes, stream);
+  cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), hit_bytes + bm_bytes, pool, stream);
   if (e != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(scratch + hit_bytes, 0, bm_bytes, stream)) != cudaSuccess) return e;
   if ((e = cudaMemsetAsync(a.dst, 0, (size_t)a.batch * a.poly_bytes, stream)) != cudaSuccess) return e;  // core.hpp:383
@@ -412,7 +412,7 @@ cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream) {
   return e;
 }
 
-cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream) {
+cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream, cudaMemPool_t pool) {
   const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
   if (total == 0) return cudaSuccess;
   uint64_t blocks = (total + 255) / 256;
@@ -421,7 +421,7 @@ cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStrea
     case SAMPLE_UNIFORM: uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
     case SAMPLE_NON_UNIFORM: non_uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
     case SAMPLE_ZO: zo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
-    case SAMPLE_HWT: return launch_hwt(a, stream);
+    case SAMPLE_HWT: return launch_hwt(a, stream, pool);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

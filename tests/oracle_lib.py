@@ -7,7 +7,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnflref.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libnflref.so")               # -march=x86-64-v3: runs on any AVX2 host
+REF_NATIVE_DIR = os.path.join(ROOT, "oracle", "_ref", "native")               # -march=native of the machine that built it
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 DTYPES = {16: np.uint16, 32: np.uint32, 64: np.uint64}
@@ -147,14 +148,34 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+def ref_native_usable():
+    """True when oracle/_ref/native (the reference's own -march=native -mtune=native build, CMakeCompilers.txt:17-24) was made
+    on a CPU whose feature flags this host has too, i.e. it is the stated build for this host and cannot hit an illegal instruction."""
+    try:
+        with open(os.path.join(REF_NATIVE_DIR, "cpu_flags.txt")) as f:
+            built = set(f.read().split(":", 1)[1].split())
+        with open("/proc/cpuinfo") as f:
+            here = next(set(line.split(":", 1)[1].split()) for line in f if line.startswith("flags"))
+    except (OSError, StopIteration, IndexError):
+        return False
+    return built <= here and os.path.exists(os.path.join(REF_NATIVE_DIR, "libnflref.so"))
+
+
+def ref_dir():
+    return REF_NATIVE_DIR if ref_native_usable() else os.path.dirname(REF_SO)
+
+
 class Ref:
-    """The unmodified reference compiled into oracle/_ref/libnflref.so (oracle/ref_harness.cpp)."""
+    """The unmodified reference compiled into oracle/_ref[/native]/libnflref.so (oracle/ref_harness.cpp)."""
     _lib = None
+    arch = None  # "-march=native" or "-march=x86-64-v3", whichever build was loaded
 
     @classmethod
     def lib(cls):
         if cls._lib is None:
-            L = ctypes.CDLL(REF_SO)
+            native = ref_native_usable()
+            cls.arch = "-march=native -mtune=native" if native else "-march=x86-64-v3 -mtune=generic"
+            L = ctypes.CDLL(os.path.join(ref_dir(), "libnflref.so"))
             L.nflref_run.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t] + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_int]
             L.nflref_build_flags.restype = ctypes.c_char_p
             cls._lib = L

@@ -17,10 +17,9 @@ CONFIGS = ["8_60_uint32_t", "128_14_uint16_t", "1024_60_uint32_t", "8192_124_uin
 ALL = [p + c for p in PROGRAMS for c in CONFIGS] + ["ntt_perfs"]
 
 # The reference's demo programs (tests/nfllib_demo_main_{op,func}.cpp: every operator, every sampler incl. the Gaussian, the
-# SIMD-vs-serial mulmod_shoup check through ops::make_op, and the LWE encrypt / decrypt self-check) and its multiple-definition
-# check (multi0.cpp + multi1.cpp) also compile and link UNCHANGED against the drop-in header.  They were added after this
-# round's GPU budget was spent, so for now they are compile-and-link evidence: running them on the device is the first
-# item of the next round (they are deliberately not in ALL).
+# SIMD-vs-serial mulmod_shoup check through ops::make_op :61-87, and the LWE encrypt / decrypt self-check :260-331, which
+# abort the program when they fail) and its multiple-definition check (multi0.cpp + multi1.cpp) compile and link UNCHANGED
+# against the drop-in header and run on the device (first run: profiles/r02a_reference_demos.txt).
 DEMOS = [d + c for d in ("nfllib_demo_main_op", "nfllib_demo_main_func") for c in ("1024_60_uint32_t", "8192_124_uint64_t")] + ["ntt_multi"]
 
 needs_build = pytest.mark.skipif(not os.path.isdir(REFDIR), reason="tests/cpp/_ref not built (needs /root/reference at build time)")
@@ -58,6 +57,19 @@ def test_reference_programs_fail_loudly_without_a_device():
 def test_reference_program_passes(binary):
     r = subprocess.run([os.path.join(REFDIR, binary)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+
+
+@pytest.mark.gpu
+@needs_build
+@pytest.mark.parametrize("binary", DEMOS)
+def test_reference_demo_program_passes(binary):
+    """Exit status 0 means the demo's own checks held: tests/nfllib_demo_main_op.cpp:61-87 compares mulmod_shoup through the
+    explicit functor with the operator path coefficient by coefficient, :260-331 encrypts and decrypts an LWE sample and
+    requires the error to vanish; both print a message and return nonzero otherwise."""
+    r = subprocess.run([os.path.join(REFDIR, binary)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    if binary != "ntt_multi":
+        assert "Time per LWE-like symmetric decryption" in r.stdout or "Time per polynomial multiplication" in r.stdout, r.stdout[-500:]
 
 
 @pytest.mark.gpu
