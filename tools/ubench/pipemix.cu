@@ -25,7 +25,7 @@ constexpr int ILP = 8;
 #define FFMA(i)  asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(g[i]) : "f"(h[i]), "f"(h[(i + 1) % ILP]))
 #define ADD64(i) asm volatile("add.u64 %0, %0, %1;" : "+l"(acc2[i]) : "l"(acc[i]))
 
-template <int MODE> __global__ void __launch_bounds__(512, 1) k(u64 *out, const u32 *seed, int iters, u32 ku) {
+template <int MODE> __global__ void __launch_bounds__(128) k(u64 *out, const u32 *seed, int iters, u32 ku) {
   u64 acc[ILP], acc2[ILP]; u32 a[ILP], b[ILP], c[ILP], d[ILP], e[ILP], f[ILP]; double x[ILP], y[ILP], z[ILP]; float g[ILP], h[ILP];
 #pragma unroll
   for (int i = 0; i < ILP; ++i) {
@@ -69,20 +69,33 @@ template <int MODE> __global__ void __launch_bounds__(512, 1) k(u64 *out, const 
         else if (MODE == 33) { DFMA(i); IMAD(i); ADD3(i); }
         else if (MODE == 34) { DFMA(i); DFMA(i); WIDE(i); ADD3(i); ADD3B(i); }
         else if (MODE == 35) { DFMA(i); FFMA(i); }
-        else if (MODE == 40) {  // today's butterfly mix: 6 WIDE + 4 IMAD + 12 ALU
-          WIDE(i); ADD3(i); WIDE(i); ADD3B(i); WIDE(i); LOP(i); WIDE(i); ADD3(i); WIDE(i); ADD3B(i); WIDE(i); LOP(i);
-          IMAD(i); ADD3(i); IMAD(i); ADD3B(i); IMAD(i); LOP(i); IMAD(i); ADD3(i); ADD3B(i); LOP(i);
+        else if (MODE >= 40) { }
+      }
+      if (MODE >= 40) {
+#define REP(OP) _Pragma("unroll") for (int i = 0; i < 4; ++i) { OP(i); }
+        if (MODE == 40) {  // today's butterfly mix: 6 WIDE + 4 IMAD + 12 ALU, op-major over 4 independent chains
+          REP(WIDE) REP(ADD3) REP(WIDE) REP(ADD3B) REP(WIDE) REP(LOP) REP(WIDE) REP(ADD3) REP(WIDE) REP(ADD3B) REP(WIDE) REP(LOP)
+          REP(IMAD) REP(ADD3) REP(IMAD) REP(ADD3B) REP(IMAD) REP(LOP) REP(IMAD) REP(ADD3) REP(ADD3B) REP(LOP)
         } else if (MODE == 41) {  // the same multiplies, 8 ALU
-          WIDE(i); ADD3(i); WIDE(i); ADD3B(i); WIDE(i); LOP(i); WIDE(i); ADD3(i); WIDE(i); ADD3B(i); WIDE(i); LOP(i);
-          IMAD(i); ADD3(i); IMAD(i); ADD3B(i); IMAD(i); IMAD(i);
-        } else if (MODE == 42) {  // the same multiplies alone
-          WIDE(i); WIDE(i); WIDE(i); WIDE(i); WIDE(i); WIDE(i); IMAD(i); IMAD(i); IMAD(i); IMAD(i);
+          REP(WIDE) REP(ADD3) REP(WIDE) REP(ADD3B) REP(WIDE) REP(LOP) REP(WIDE) REP(ADD3) REP(WIDE) REP(ADD3B) REP(WIDE) REP(LOP)
+          REP(IMAD) REP(ADD3) REP(IMAD) REP(ADD3B) REP(IMAD) REP(IMAD)
+        } else if (MODE == 42) {  // the multiplies alone
+          REP(WIDE) REP(WIDE) REP(WIDE) REP(WIDE) REP(WIDE) REP(WIDE) REP(IMAD) REP(IMAD) REP(IMAD) REP(IMAD)
         } else if (MODE == 43) {  // FP64-quotient butterfly mix: 2 WIDE + 4 IMAD + 11 DFMA + 14 ALU
-          WIDE(i); DFMA(i); ADD3(i); DFMA(i); ADD3B(i); WIDE(i); DFMA(i); LOP(i); DFMA(i); ADD3(i); IMAD(i); DFMA(i); ADD3B(i); DFMA(i); LOP(i);
-          IMAD(i); DFMA(i); ADD3(i); DFMA(i); ADD3B(i); IMAD(i); DFMA(i); LOP(i); DFMA(i); ADD3(i); IMAD(i); DFMA(i); ADD3B(i); LOP(i); ADD3(i); ADD3B(i);
+          REP(WIDE) REP(DFMA) REP(ADD3) REP(DFMA) REP(ADD3B) REP(WIDE) REP(DFMA) REP(LOP) REP(DFMA) REP(ADD3) REP(IMAD) REP(DFMA) REP(ADD3B) REP(DFMA) REP(LOP)
+          REP(IMAD) REP(DFMA) REP(ADD3) REP(DFMA) REP(ADD3B) REP(IMAD) REP(DFMA) REP(LOP) REP(DFMA) REP(ADD3) REP(IMAD) REP(DFMA) REP(ADD3B) REP(LOP) REP(ADD3) REP(ADD3B)
         } else if (MODE == 44) {  // 12 ALU alone
-          ADD3(i); ADD3B(i); LOP(i); ADD3(i); ADD3B(i); LOP(i); ADD3(i); ADD3B(i); LOP(i); ADD3(i); ADD3B(i); LOP(i);
+          REP(ADD3) REP(ADD3B) REP(LOP) REP(ADD3) REP(ADD3B) REP(LOP) REP(ADD3) REP(ADD3B) REP(LOP) REP(ADD3) REP(ADD3B) REP(LOP)
+        } else if (MODE == 45) {  // 12 ALU with one register operand + immediate
+          REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI) REP(ADDI)
+        } else if (MODE == 46) {  // multiplies + 12 one-register ALU
+          REP(WIDE) REP(ADDI) REP(WIDE) REP(ADDI) REP(WIDE) REP(ADDI) REP(WIDE) REP(ADDI) REP(WIDE) REP(ADDI) REP(WIDE) REP(ADDI)
+          REP(IMAD) REP(ADDI) REP(IMAD) REP(ADDI) REP(IMAD) REP(ADDI) REP(IMAD) REP(ADDI) REP(ADDI) REP(ADDI)
+        } else if (MODE == 47) {  // multiplies + 12 two-register ALU
+          REP(WIDE) REP(ADD2) REP(WIDE) REP(ADD2) REP(WIDE) REP(ADD2) REP(WIDE) REP(ADD2) REP(WIDE) REP(ADD2) REP(WIDE) REP(ADD2)
+          REP(IMAD) REP(ADD2) REP(IMAD) REP(ADD2) REP(IMAD) REP(ADD2) REP(IMAD) REP(ADD2) REP(ADD2) REP(ADD2)
         }
+#undef REP
       }
     }
   }
@@ -95,15 +108,18 @@ template <int MODE> __global__ void __launch_bounds__(512, 1) k(u64 *out, const 
 template <int MODE> void run(const char *name, u64 *out, const u32 *seed) {
   const int iters = 1500;
   printf("%-78s", name);
-  for (int wps = 4; wps <= 16; wps += 4) {  // warps per sub-partition (one CTA per SM)
-    const int threads = wps * 4 * 32;
-    k<MODE><<<148, threads>>>(out, seed, 10, 3u);
+  for (int wps = 4; wps <= 16; wps += 4) {  // warps per sub-partition: wps CTAs of 4 warps per SM (registers permitting)
+    const int threads = 128;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k<MODE>, threads, 0);
+    if (occ < wps) { printf(" %7s", "-"); continue; }
+    k<MODE><<<148 * wps, threads>>>(out, seed, 10, 3u);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
-    k<MODE><<<148, threads>>>(out, seed, iters, 3u);
+    k<MODE><<<148 * wps, threads>>>(out, seed, iters, 3u);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    const double groups_per_smsp = (double)iters * 2 * ILP * wps;
+    const double groups_per_smsp = (double)iters * 2 * (MODE >= 40 ? 4 : ILP) * wps;  // (the mixes of a butterfly run 4 chains, op-major)
     printf(" %7.2f", ms * 1e-3 * 1.965e9 / groups_per_smsp);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
@@ -111,7 +127,7 @@ template <int MODE> void run(const char *name, u64 *out, const u32 *seed) {
 }
 
 int main() {
-  u64 *out; u32 *seed; cudaMalloc(&out, (size_t)148 * 512 * 8); cudaMalloc(&seed, 1024);
+  u64 *out; u32 *seed; cudaMalloc(&out, (size_t)148 * 16 * 128 * 8); cudaMalloc(&seed, 1024);
   u32 h[256]; for (int i = 0; i < 256; ++i) h[i] = 0x9E3779B9u * (i + 1); cudaMemcpy(seed, h, 1024, cudaMemcpyHostToDevice);
   printf("%-78s %7s %7s %7s %7s   (cycles per group per sub-partition at 1.965 GHz; warps per sub-partition)\n", "group", "4", "8", "12", "16");
   run<0>("WIDE (mad.wide.u32, 64-bit accumulate)", out, seed);
@@ -148,7 +164,10 @@ int main() {
   run<42>("6 WIDE + 4 IMAD (a butterfly's multiplies)", out, seed);
   run<41>("6 WIDE + 4 IMAD + 8 ALU", out, seed);
   run<40>("6 WIDE + 4 IMAD + 12 ALU (today's butterfly)", out, seed);
-  run<44>("12 ALU", out, seed);
+  run<44>("12 ALU (three register operands)", out, seed);
+  run<45>("12 ALU (one register + immediate)", out, seed);
+  run<46>("6 WIDE + 4 IMAD + 12 one-register ALU", out, seed);
+  run<47>("6 WIDE + 4 IMAD + 12 two-register ALU", out, seed);
   run<43>("2 WIDE + 4 IMAD + 11 DFMA + 14 ALU (FP64-quotient butterfly)", out, seed);
   printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
