@@ -475,6 +475,13 @@ template <class C> __device__ __forceinline__ void next_unit_prefetch(const Unit
 
 // ---- kernels -------------------------------------------------------------------------------------------------
 
+#ifdef NFLGPU_TRACE
+// experiment builds only (tools/variants.sh ... -DNFLGPU_TRACE): when does every unit slot of the forward kernel finish?
+// [0] = earliest CTA start (globaltimer, ns), [1 + cta * SLOTS + slot] = that slot's finish time
+static __device__ unsigned long long nflgpu_trace_buf[1 + 8192];
+__device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
+
 template <class C> __device__ __forceinline__ const typename C::TW *stage_twiddles(const NttArgs &a, int cm, unsigned char *smem) {
   typedef typename C::TW TW;
   const TW *twg = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::N;
@@ -513,6 +520,9 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 
   // one iteration = one sub-block (= one whole unit when SPLIT == 0)
   const uint32_t nblocks = a.batch << C::LOGG;  // the launcher keeps batch << LOGG below 2^31
+#ifdef NFLGPU_TRACE
+  if (threadIdx.x == 0) atomicMin(&nflgpu_trace_buf[0], trace_now());
+#endif
   UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
   for (; walk.index() < nblocks; walk.advance()) {
     walk.claim_ahead();
@@ -546,6 +556,9 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
       else tile_to_gmem<C>(tile, dst + bbase, tl);
     }
   }
+#ifdef NFLGPU_TRACE
+  if (tl == 0 && blockIdx.x * C::SLOTS + slot < 8192) nflgpu_trace_buf[1 + blockIdx.x * C::SLOTS + slot] = trace_now();
+#endif
   UnitWalk<C>::finish(a);
 }
 

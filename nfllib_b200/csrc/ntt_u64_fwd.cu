@@ -13,3 +13,14 @@ cudaError_t launch_ntt_u64_fwd(int log2_degree, const NttLaunch &l, int device, 
   return cudaErrorInvalidValue;
 }
 }  // namespace nflgpu
+#ifdef NFLGPU_TRACE
+extern "C" int nflgpu_debug_trace(unsigned long long *out, int n, int reset) {
+  if (out && cudaMemcpyFromSymbol(out, nflgpu::nflgpu_trace_buf, sizeof(unsigned long long) * (size_t)n) != cudaSuccess) return -3;
+  if (reset) {
+    static unsigned long long init[1 + 8192];
+    init[0] = ~0ull;
+    if (cudaMemcpyToSymbol(nflgpu::nflgpu_trace_buf, init, sizeof(init)) != cudaSuccess) return -3;
+  }
+  return 0;
+}
+#endif

@@ -42,3 +42,15 @@ def test_dropin_program_matches_oracle(limb, tmp_path):
     exp = np.concatenate([exp_single] + [x.reshape(-1) for x in batch])
     assert got.size == exp.size
     assert np.array_equal(got, exp)
+
+
+STRESS = os.path.join(ROOT, "tests", "cpp", "sched_stress")
+
+
+@pytest.mark.gpu
+def test_scheduler_stress_program_without_torch():
+    """tests/cpp/sched_stress.cpp: hundreds of forward / inverse launches of the dynamically scheduled and the split sizes on two
+    non-blocking streams, through the C ABI only (the program compute-sanitizer racecheck runs: profiles/r02c_sanitizers.txt)."""
+    assert os.path.exists(STRESS), "run __graft_entry__.build()"
+    r = subprocess.run([STRESS, "200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout, r.stdout + r.stderr
