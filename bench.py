@@ -558,6 +558,16 @@ def run_b200(args):
     e2e_pg_s = timed_host(e2e_pageable_step, pg_steps)
     e2e_pg_ok = bool(np.array_equal(pB[:2], o.run("fwd", pA[:2])))
 
+    # ... and after page-locking those same arrays once (nflgpu_host_register = cudaHostRegister): direct DMA, no staging
+    t0 = time.perf_counter()
+    for arr in (pA, pD, pB, pC):
+        ctx.host_register(arr)
+    register_ms = (time.perf_counter() - t0) * 1e3
+    e2e_reg_s = timed_host(e2e_pageable_step, pg_steps)
+    e2e_reg_ok = bool(np.array_equal(pB[:2], o.run("fwd", pA[:2])))
+    for arr in (pA, pD, pB, pC):
+        ctx.host_unregister(arr)
+
     # copy-only ceiling of this box, same process, same bytes per step as e2e (2 x 128 MiB each way), both directions at once
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
 
@@ -607,7 +617,11 @@ def run_b200(args):
                        "api": "nflgpu_host_op(fwd) + nflgpu_host_op(inv) on pinned host buffers", "checked_vs_oracle": e2e_ok,
                        "pageable": {"value": 2.0 * BATCH * world * pg_steps / e2e_pg_s, "unit": UNIT, "checked_vs_oracle": e2e_pg_ok,
                                     "what": "the same two calls on pageable numpy arrays (the layout of posix_memalign'ed nfl::poly[]): "
-                                            "staged through the library's pinned buffers"},
+                                            "staged through the library's pinned buffers by a few host threads"},
+                       "pageable_registered": {"value": 2.0 * BATCH * world * pg_steps / e2e_reg_s, "unit": UNIT, "checked_vs_oracle": e2e_reg_ok,
+                                               "register_ms_once": register_ms,
+                                               "what": "the same arrays after one nflgpu_host_register each (4 x 128 MiB page-locked in "
+                                                       "register_ms_once, outside the timed region): direct DMA"},
                        "copy_only_ceiling": {"value": ceiling, "unit": UNIT, "frac_reached": e2e_value / ceiling,
                                              "what": "cudaMemcpyAsync of the same bytes per step, H2D and D2H on two streams at once, "
                                                      "no kernel, all ranks together: what the box's PCIe / host memory allows"},

@@ -496,8 +496,9 @@ public:
   void set(hwt_dist const &mode) {
     detail::prng_state &g = detail::prng_state::get();
     detail::dev_buf<poly> b(1);
-    const uint64_t refills = mode.hwt ? (degree - mode.hwt + mode.hwt - 1) / mode.hwt + 1 : 1;  // nonces one draw consumes (nflgpu.h)
-    detail::check(nflgpu_hwt(backend_type::get().ctx, b.p, 1, mode.hwt, g.key, g.take(refills), nullptr), "nflgpu_hwt");
+    uint64_t used = 0;  // nonces the draw consumed: data dependent in the (rare) case of a rejected index, like the reference
+    detail::check(nflgpu_hwt_count(backend_type::get().ctx, b.p, 1, mode.hwt, g.key, g.nonce.load(), &used, nullptr), "nflgpu_hwt");
+    g.take(used);
     fetch(b);
   }
   void set(ZO_dist const &mode) {
@@ -810,6 +811,27 @@ template <class T, size_t D, size_t M> std::ostream &operator<<(std::ostream &os
 // Device-resident batches: the throughput API.  `count` polys stay in HBM in exactly the layout of poly[count].
 // ---------------------------------------------------------------------------------------------------------
 namespace cuda {
+
+// Whole host arrays of polys through the chunked, double-buffered host pipeline (nflgpu_host_op): what a loop of
+// p[i].ntt_pow_phi() over a contiguous array should be written as.  In place.
+template <class P> void ntt_pow_phi(P *polys, size_t count) {
+  detail::check(nflgpu_host_op(P::backend_type::get().ctx, 0, polys, polys, nullptr, nullptr, count), "ntt_pow_phi[]");
+}
+template <class P> void invntt_pow_invphi(P *polys, size_t count) {
+  detail::check(nflgpu_host_op(P::backend_type::get().ctx, 1, polys, polys, nullptr, nullptr, count), "invntt_pow_invphi[]");
+}
+// Page-locks a host array of polys for the lifetime of the guard (nflgpu_host_register): the host-buffer calls above then
+// DMA it directly instead of staging it through pinned buffers.  Destroy the guard before freeing the array.
+template <class P> class pinned_region {
+  void *p_;
+public:
+  pinned_region(P *polys, size_t count) : p_(polys) {
+    detail::check(nflgpu_host_register(P::backend_type::get().ctx, polys, count * sizeof(P)), "nflgpu_host_register");
+  }
+  ~pinned_region() { nflgpu_host_unregister(P::backend_type::get().ctx, p_); }
+  pinned_region(const pinned_region &) = delete;
+  pinned_region &operator=(const pinned_region &) = delete;
+};
 
 template <class P> class batch {
   detail::dev_buf<P> buf_;

@@ -171,10 +171,15 @@ int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_
  * each, from one keystream byte per coefficient; -1 / +1 are stored as p_cm - 1 / p_cm + 1 exactly as the reference does. */
 int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream);
 /* poly::set(nfl::hwt_dist(hwt)) (core.hpp:355-392, poly.hpp:54-57): exactly `hwt` coefficients are +-1 (p_cm - 1 / p_cm + 1),
- * chosen by reservoir sampling with rejection-sampled indices.  Each polynomial consumes ceil((degree - hwt) / hwt) + 1
- * fastrandombytes calls (nonces): polynomial i starts at first_nonce + i * that count, which is the reference's nonce
- * sequence (an index rejection exactly at a refill boundary, probability < 2^-44 per draw, would shift the reference's). */
+ * chosen by reservoir sampling with rejection-sampled indices.  A polynomial normally consumes ceil((degree - hwt) / hwt) + 1
+ * fastrandombytes calls (nonces); an index rejection (probability < 2^-44 per draw) can cost one more, which moves the start
+ * of every later polynomial in the reference's sequential stream.  The device draws all polynomials in parallel from the
+ * normal starts, then a repair kernel (idle unless that happened) re-draws what a longer polynomial displaced: the result is
+ * the reference's nonce sequence in every case.  nflgpu_hwt_count also reports the nonces the batch consumed (where the stream
+ * continues) and synchronises `stream` to do so; nflgpu_hwt is the asynchronous form. */
 int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce, void *stream);
+int nflgpu_hwt_count(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce,
+                     uint64_t *nonces_used, void *stream);
 
 /* poly::set(nfl::gaussian<in_class, T, lu_depth>(&prng, amplifier)) (core.hpp:284-325, poly.hpp:61-67) over
  * nfl::FastGaussianNoise<in_class, T, lu_depth>(sigma, security, samples, center) (prng/FastGaussianNoise.hpp).
@@ -251,6 +256,12 @@ int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *s
  * one context per host thread. */
 int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host,
                    const void *c_host, size_t batch);
+/* Pageable host arrays (e.g. posix_memalign'ed nfl::poly[], tests/tools.h:6-17) go through pinned staging buffers with an extra
+ * host copy each way (a few host threads, NFLGPU_HOST_COPY_THREADS).  A caller that keeps its arrays can page-lock them once
+ * instead — nflgpu_host_register is cudaHostRegister without the CUDA headers — after which nflgpu_host_op DMAs them directly,
+ * like memory from cudaHostAlloc.  Unregister before freeing the memory. */
+int nflgpu_host_register(nflgpu_ctx *ctx, void *host_ptr, size_t bytes);
+int nflgpu_host_unregister(nflgpu_ctx *ctx, void *host_ptr);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,7 @@ def lib():
         L.nflgpu_non_uniform.argtypes = [vp, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_zo.argtypes = [vp, vp, sz, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_hwt.argtypes = [vp, vp, sz, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, vp]
+        L.nflgpu_hwt_count.argtypes = [vp, vp, sz, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64, u64p, vp]
         i64p = ctypes.POINTER(ctypes.c_int64)
         L.nflgpu_gaussian_create.argtypes = [ctypes.POINTER(vp), vp, ctypes.c_double, ctypes.c_uint, ctypes.c_uint, ctypes.c_double, ci, ci]
         L.nflgpu_gaussian_create_from_barriers.argtypes = [ctypes.POINTER(vp), vp, vp, sz, sz, ci, ci, ctypes.c_int64]
@@ -72,6 +73,8 @@ def lib():
         L.nflgpu_poly2mpz.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_mpz2poly.argtypes = [vp, vp, vp, sz, vp]
         L.nflgpu_eval.argtypes = [vp, vp, ctypes.POINTER(vp), sz, ctypes.c_char_p, sz, sz, vp]
+        L.nflgpu_host_register.argtypes = [vp, vp, sz]
+        L.nflgpu_host_unregister.argtypes = [vp, vp]
         L.nflgpu_scratch_alloc.argtypes = [vp, sz, ctypes.POINTER(vp), vp]
         L.nflgpu_scratch_free.argtypes = [vp, vp, vp]
         L.nflgpu_ctx_trim.argtypes = [vp]
@@ -247,6 +250,12 @@ class Context:
     def hwt(self, dst, batch, hwt, key, first_nonce, stream=0):
         _check(lib().nflgpu_hwt(self.h, dst, batch, hwt, bytes(key), first_nonce, stream))
 
+    def hwt_count(self, dst, batch, hwt, key, first_nonce, stream=0):
+        """nflgpu_hwt_count: like hwt(), returns the number of nonces the batch consumed (synchronises the stream)."""
+        used = ctypes.c_uint64()
+        _check(lib().nflgpu_hwt_count(self.h, dst, batch, hwt, bytes(key), first_nonce, ctypes.byref(used), stream))
+        return used.value
+
     def zo(self, dst, batch, rho, key, first_nonce, stream=0):
         _check(lib().nflgpu_zo(self.h, dst, batch, rho, bytes(key), first_nonce, stream))
 
@@ -323,6 +332,13 @@ class Context:
                                     None if ops[0] is None else ops[0].ctypes.data,
                                     None if ops[1] is None else ops[1].ctypes.data, batch))
         return out
+
+    def host_register(self, array):
+        """nflgpu_host_register: page-lock a numpy array so that host_op DMAs it directly."""
+        _check(lib().nflgpu_host_register(self.h, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array):
+        _check(lib().nflgpu_host_unregister(self.h, array.ctypes.data))
 
     # ---- convenience for tests: run a device-resident op on numpy data through alloc/upload/.../download ----
     def run_device(self, op, a, b=None, c=None, d=None, inplace=False):

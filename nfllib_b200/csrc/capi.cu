@@ -15,6 +15,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -632,7 +633,7 @@ int nflgpu_mpz2poly(nflgpu_ctx *ctx, void *dst_polys, const uint64_t *src_words,
 }
 
 static int run_sampler(nflgpu_ctx *ctx, int kind, void *dst, size_t batch, const uint8_t *key, uint64_t first_nonce, uint64_t p0,
-                       uint64_t p1, uint64_t p2, size_t stream_bytes, void *stream) {
+                       uint64_t p1, uint64_t p2, size_t stream_bytes, void *stream, unsigned long long *hwt_used = nullptr) {
   int rc;
   if ((rc = check_buf(ctx, dst, "dst"))) return rc;
   if (!key) { set_error("null key"); return NFLGPU_ERR_ARG; }
@@ -650,7 +651,8 @@ static int run_sampler(nflgpu_ctx *ctx, int kind, void *dst, size_t batch, const
   a.nmoduli = (uint32_t)ctx->nmoduli; a.log2_degree = (uint32_t)ctx->log2_degree; a.limb_bits = (uint32_t)ctx->limb_bits;
   a.batch = (uint32_t)batch;
   a.param0 = p0; a.param1 = p1; a.param2 = p2;
-  CUDA_TRY(launch_sampler(kind, a, ctx->num_sms, (cudaStream_t)stream, ctx->pool));
+  CUDA_TRY(launch_sampler(kind, a, ctx->num_sms, (cudaStream_t)stream, ctx->pool, hwt_used));
+  if (kind == SAMPLE_HWT) ctx->launches++;  // the draw and the (normally idle) repair kernel
   ctx->launches++;
   return NFLGPU_OK;
 }
@@ -671,11 +673,25 @@ int nflgpu_non_uniform(nflgpu_ctx *ctx, void *dst, size_t batch, uint64_t upper_
   return run_sampler(ctx, SAMPLE_NON_UNIFORM, dst, batch, key, first_nonce, upper_bound, amplifier, mask, ctx->degree * ctx->limb_bytes, stream);
 }
 
-int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+int nflgpu_hwt_count(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce,
+                     uint64_t *nonces_used, void *stream) {
   if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
   if (hwt == 0 || hwt > ctx->degree) { set_error("hwt must be in [1, degree]"); return NFLGPU_ERR_ARG; }  // core.hpp:356
   const uint64_t calls = (ctx->degree - hwt + hwt - 1) / hwt + 1;  // refills of hwt words + the sign keystream
-  return run_sampler(ctx, SAMPLE_HWT, dst, batch, key, first_nonce, hwt, calls, 0, 64, stream);
+  uint64_t shift = 0;  // testing aid: shrink the rejection sampler's acceptance range so that tests can force extra refills
+  if (const char *e = std::getenv("NFLGPU_HWT_TEST_REJECT_SHIFT")) shift = (uint64_t)std::strtoull(e, nullptr, 10) & 63;
+  if (nonces_used) *nonces_used = 0;
+  unsigned long long used = 0;
+  int rc = run_sampler(ctx, SAMPLE_HWT, dst, batch, key, first_nonce, hwt, calls, shift, 64, stream, nonces_used ? &used : nullptr);
+  if (rc != NFLGPU_OK || !nonces_used || batch == 0) return rc;
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  *nonces_used = used;
+  return NFLGPU_OK;
+}
+
+int nflgpu_hwt(nflgpu_ctx *ctx, void *dst, size_t batch, uint32_t hwt, const uint8_t key[32], uint64_t first_nonce, void *stream) {
+  return nflgpu_hwt_count(ctx, dst, batch, hwt, key, first_nonce, nullptr, stream);
 }
 
 int nflgpu_zo(nflgpu_ctx *ctx, void *dst, size_t batch, uint8_t rho, const uint8_t key[32], uint64_t first_nonce, void *stream) {
@@ -923,6 +939,43 @@ int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *s
 
 // ---- host-buffer pipeline ------------------------------------------------------------------------------------
 
+// Staging copies between pageable user memory and the pinned buffers: one host thread moves ~8-10 GB/s, which would cap the
+// pageable path far below PCIe; a few threads on disjoint slices bring it to the DMA rate (NFLGPU_HOST_COPY_THREADS, default 4).
+static void staging_copy(void *dst, const void *src, size_t bytes) {
+  static const unsigned want = [] {
+    const char *e = std::getenv("NFLGPU_HOST_COPY_THREADS");
+    long v = e ? std::atol(e) : 4;
+    return (unsigned)(v < 1 ? 1 : v > 16 ? 16 : v);
+  }();
+  const unsigned nt = bytes >= ((size_t)2 << 20) ? want : 1;
+  if (nt == 1) { std::memcpy(dst, src, bytes); return; }
+  const size_t slice = ((bytes / nt) + 4095) & ~(size_t)4095;
+  std::thread th[16];
+  unsigned started = 0;
+  for (unsigned t = 1; t < nt; ++t) {
+    const size_t off = (size_t)t * slice;
+    if (off >= bytes) break;
+    const size_t len = bytes - off < slice ? bytes - off : slice;
+    th[started++] = std::thread([=] { std::memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
+  }
+  std::memcpy(dst, src, slice < bytes ? slice : bytes);
+  for (unsigned t = 0; t < started; ++t) th[t].join();
+}
+
+int nflgpu_host_register(nflgpu_ctx *ctx, void *host_ptr, size_t bytes) {
+  if (!ctx || !host_ptr || bytes == 0) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaHostRegister(host_ptr, bytes, cudaHostRegisterDefault));
+  return NFLGPU_OK;
+}
+
+int nflgpu_host_unregister(nflgpu_ctx *ctx, void *host_ptr) {
+  if (!ctx || !host_ptr) { set_error("null argument"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  CUDA_TRY(cudaHostUnregister(host_ptr));
+  return NFLGPU_OK;
+}
+
 static bool is_pinned(const void *p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -1021,7 +1074,7 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
     HostStage &s = ctx->stage[k];
     if (pend[k].active) {  // retire the chunk that used this stage kStages steps ago
       PIPE_TRY(cudaStreamSynchronize(s.stream));
-      if (!pinned[3]) std::memcpy(static_cast<char *>(dst_host) + pend[k].first * poly_bytes, s.pin[3], pend[k].count * poly_bytes);
+      if (!pinned[3]) staging_copy(static_cast<char *>(dst_host) + pend[k].first * poly_bytes, s.pin[3], pend[k].count * poly_bytes);
       pend[k].active = false;
     }
     if (done >= batch) continue;
@@ -1030,7 +1083,7 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
       const char *src = static_cast<const char *>(in[i]) + done * poly_bytes;
       if (!pinned[i]) {
         if (!s.pin[i]) PIPE_TRY(cudaHostAlloc(&s.pin[i], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
-        std::memcpy(s.pin[i], src, cnt * poly_bytes);
+        staging_copy(s.pin[i], src, cnt * poly_bytes);
         src = static_cast<const char *>(s.pin[i]);
       }
       PIPE_TRY(cudaMemcpyAsync(s.dev[i], src, cnt * poly_bytes, cudaMemcpyHostToDevice, s.stream));

@@ -74,18 +74,19 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int PADW = VEC;                       // 16 bytes of padding per row of E words
   static constexpr int ROW = E + PADW;
   static constexpr int TILE_WORDS = (NP - SPLIT > 1) ? (B >> e) * ROW : 0;
-  // CTA size: 256 threads (2+ CTAs per SM); 512 for N = 1024 x 64-bit (8 two-warp units per CTA, measured best)
+  // CTA size: 256 threads (2+ CTAs per SM)
 #ifdef NFLGPU_TARGET_THREADS
   static constexpr int TARGET_THREADS = NFLGPU_TARGET_THREADS;
 #else
-  static constexpr int TARGET_THREADS = (LB == 64 && LOGN == 10) ? 512 : 256;
+  // N = 1024 x 64-bit: one CTA of 1024 threads per SM (16 two-warp units) measured 3.6 % faster than two CTAs of 512 (profiles/r02_variants.log)
+  static constexpr int TARGET_THREADS = (LB == 64 && LOGN == 10) ? 1024 : 256;
 #endif
   static constexpr int SLOTS = (TPU >= TARGET_THREADS) ? 1 : TARGET_THREADS / TPU;
   static constexpr int THREADS = TPU * SLOTS;
 #ifdef NFLGPU_MIN_BLOCKS
   static constexpr int MIN_BLOCKS = NFLGPU_MIN_BLOCKS;
 #else
-  static constexpr int MIN_BLOCKS = (LB == 64 && LOGN == 10) ? 2 : (THREADS <= 256) ? ((WB == 32 && E <= 32) ? 4 : 2) : 1;
+  static constexpr int MIN_BLOCKS = (THREADS <= 256) ? ((WB == 32 && E <= 32) ? 4 : 2) : 1;
 #endif
   static constexpr bool TW_SMEM = SPLIT == 0 && (size_t)N * sizeof(TW) <= 32768;
   static constexpr size_t TW_BYTES = TW_SMEM ? (size_t)N * sizeof(TW) : 0;
@@ -111,6 +112,17 @@ template <int LB, int LOGN> struct NttCfg {
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------
+
+// Coefficient loads.  The kernels support dst == src (nflgpu_polymul's inverse, batch::ntt_pow_phi): every word of a slab is read
+// exactly once, by the unit that later overwrites it, before any of that unit's stores -- the invariant that makes the
+// non-coherent path (ld.global.nc) legal there.  -DNFLGPU_PLAIN_LD switches to ordinary loads (measured: no difference).
+template <class T> __device__ __forceinline__ T ld_coef(const T *p) {
+#ifdef NFLGPU_PLAIN_LD
+  return *p;
+#else
+  return __ldg(p);
+#endif
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -155,6 +167,9 @@ template <class C> __device__ __forceinline__ void prefetch_unit(const typename 
 }
 
 template <class C> __device__ __forceinline__ void unit_sync(int slot, int lane_base) {
+#if defined(NFLGPU_ABL) && (NFLGPU_ABL & 4)  // timing experiment: no barriers between the passes (results are wrong)
+  return;
+#endif
   if (C::TPU >= 64) {
     if (C::SLOTS == 1) __syncthreads();
     else asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(C::TPU) : "memory");
@@ -349,9 +364,9 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
     const int pos = ch * C::VEC;
     uint4 t;
     if (sizeof(Store) == sizeof(Word)) {
-      t = __ldg(reinterpret_cast<const uint4 *>(g + pos));
+      t = ld_coef(reinterpret_cast<const uint4 *>(g + pos));
     } else {
-      const uint2 i = __ldg(reinterpret_cast<const uint2 *>(g + pos));
+      const uint2 i = ld_coef(reinterpret_cast<const uint2 *>(g + pos));
       t.x = i.x & 0xffffu; t.y = i.x >> 16; t.z = i.y & 0xffffu; t.w = i.y >> 16;
     }
     *reinterpret_cast<uint4 *>(tile + C::pad(pos)) = t;
@@ -367,10 +382,12 @@ template <class C, int PASS> struct FwdChain {
                                              int lane_base) {
     tile_load<C, PASS>(x, tile, tid);
     fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
+#if !(defined(NFLGPU_ABL) && (NFLGPU_ABL & 8))  // (timing experiment 8: no canonicalisation)
     if (PASS == C::NP - 1) {
 #pragma unroll
       for (int k = 0; k < C::E; ++k) x[k] = fwd_canon<C>(x[k], p, twop);
     }
+#endif
     tile_store<C, PASS>(x, tile, tid);
     if (PASS + 1 < C::NP) unit_sync<C>(slot, lane_base);
     FwdChain<C, PASS + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
@@ -533,8 +550,13 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     if (!C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // static walk: the next index is known now
     Word x[C::E];
     // the first tile pass reads straight from global memory: for fixed k the threads touch consecutive limbs
+#if defined(NFLGPU_ABL) && (NFLGPU_ABL & 1)  // timing experiment: no global loads (results are wrong)
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, S>(tid, k));
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)(ubase + pass_pos<C, S>(tid, k)) * 0x9E3779B97F4A7C15ull >> 3;
+#else
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, S>(tid, k));
+#endif
     fwd_pass<C, S>(x, pass_tw<C, S>(tw, tid), np, twop);
     if (C::NP - S == 1) {
 #pragma unroll
@@ -552,8 +574,12 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
       if (C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // the leader's claim has just been published
       FwdChain<C, S + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
+#if defined(NFLGPU_ABL) && (NFLGPU_ABL & 2)  // timing experiment: one store per unit instead of the copy-out
+      if (tl == 0) dst[bbase] = (Store)tile[0];
+#else
       if (MUL) tile_to_gmem_mul<C, LB>(tile, dst + bbase, reinterpret_cast<const Store *>(a.other) + bbase, tl, p, a.consts[cm]);
       else tile_to_gmem<C>(tile, dst + bbase, tl);
+#endif
     }
   }
 #ifdef NFLGPU_TRACE
@@ -592,7 +618,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     Word x[C::E];
     if (C::NP - S == 1) {
 #pragma unroll
-      for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, S>(tid, k));
+      for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, S>(tid, k));
     } else {
       if (!C::DYNAMIC) unit_sync<C>(slot, lane_base);  // previous sub-block's last pass has finished reading the tile (advance() syncs in dynamic mode)
       gmem_to_tile<C>(tile, src + ubase + (size_t)g * C::B, tl);
@@ -632,7 +658,7 @@ __global__ void __launch_bounds__(256) ntt_gpass_kernel(const NttArgs a) {
     const size_t ubase = (size_t)u * C::N;
     Word x[C::E];
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = (Word)__ldg(src + ubase + pass_pos<C, PASS>(tid, k));
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, PASS>(tid, k));
     if (INV) inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, np, twop, __ldg(tw + C::N - 1));
     else fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
 #pragma unroll

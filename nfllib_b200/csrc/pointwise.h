@@ -46,9 +46,10 @@ struct SampleArgs {
   uint64_t first_nonce;
   uint64_t poly_bytes, blocks_per_poly;  // blocks_per_poly = ceil(poly_bytes / 64)
   uint32_t nmoduli, log2_degree, limb_bits, batch;
-  uint64_t param0, param1, param2;  // non_uniform: upper_bound, amplifier, mask;  ZO: rho;  hwt: hwt, calls per polynomial
+  uint64_t param0, param1, param2;  // non_uniform: upper_bound, amplifier, mask;  ZO: rho;  hwt: hwt, calls per polynomial, test-only reject shift
 };
-cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream, cudaMemPool_t pool);  // pool: scratch of the hwt sampler
+// pool: scratch of the hwt sampler; hwt_used (host pointer or null): asynchronous copy of the nonces the hwt batch consumed
+cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream, cudaMemPool_t pool, unsigned long long *hwt_used = nullptr);
 
 }  // namespace nflgpu
 #endif

@@ -99,16 +99,15 @@ __global__ void __launch_bounds__(256) zo_kernel(const SampleArgs a) {
 // poly::set(hwt_dist) core.hpp:355-392: reservoir sampling is sequential inside a polynomial, so one thread draws one
 // polynomial (the batch supplies the parallelism).  `hit` and `bitmap` are scratch: the reservoir slots and the set of
 // selected positions (the reference sorts the slots; scanning the bitmap in ascending order pairs position and sign word
-// identically).  Polynomial i starts at nonce first_nonce + i * param1, param1 = ceil((N - hwt) / hwt) + 1 calls: exactly the
-// reference's nonce sequence unless an index is rejected right at a refill boundary (probability below 2^-44 per draw).
-__global__ void __launch_bounds__(64) hwt_kernel(const SampleArgs a, uint32_t *hit_all, uint32_t *bitmap_all) {
+// identically).  A polynomial normally consumes param1 = ceil((N - hwt) / hwt) + 1 fastrandombytes calls (nonces); an index
+// rejected by the rejection sampling (probability < 2^-44 per draw) can push it past a refill boundary and cost one more, which
+// shifts the start nonce of every later polynomial of the reference's sequential stream.  hwt_one returns the calls actually
+// made; hwt_kernel assumes the normal count for the starts, hwt_repair_kernel re-draws whatever a longer polynomial displaced.
+// param2 (testing aid, 0 in production) cuts the top 2^-param2 part off the acceptance range so that tests can force the case.
+__device__ uint64_t hwt_one(const SampleArgs &a, uint64_t poly, uint64_t start_nonce, uint32_t *hit, uint32_t *bitmap) {
   const uint64_t degree = 1ull << a.log2_degree;
-  const uint32_t hwt = (uint32_t)a.param0;
-  const uint64_t poly = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (poly >= a.batch) return;
-  uint32_t *hit = hit_all + poly * hwt;
-  uint32_t *bitmap = bitmap_all + poly * ((degree + 31) / 32);  // zeroed by the launcher
-  uint64_t nonce = a.first_nonce + poly * a.param1, cur = 0, blk = 0;
+  const uint32_t hwt = (uint32_t)a.param0, shift = (uint32_t)a.param2;
+  uint64_t nonce = start_nonce, cur = 0, blk = 0;
   uint32_t x[16], avail = 0, widx = 8;
   for (uint32_t k = 0; k < hwt; ++k) hit[k] = k;
   for (uint64_t k = hwt; k < degree; ++k) {
@@ -119,13 +118,13 @@ __global__ void __launch_bounds__(64) hwt_kernel(const SampleArgs a, uint32_t *h
       if (widx == 8) { salsa20_block(a.key, cur, blk++, x); widx = 0; }
       pos = ((uint64_t)x[2 * widx + 1] << 32) | x[2 * widx];
       ++widx; --avail;
-      if (pos <= reject * k) { pos %= k; break; }
+      if (pos <= reject * k - (shift ? (reject * k) >> shift : 0)) { pos %= k; break; }
     }
     if (pos < hwt) hit[pos] = (uint32_t)k;
   }
   for (uint32_t k = 0; k < hwt; ++k) atomicOr(&bitmap[hit[k] >> 5], 1u << (hit[k] & 31));
-  cur = nonce; blk = 0; widx = 8;  // the sign keystream: one more fastrandombytes call
-  unsigned char *dst = reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes;  // zeroed by the launcher
+  cur = nonce++; blk = 0; widx = 8;  // the sign keystream: one more fastrandombytes call
+  unsigned char *dst = reinterpret_cast<unsigned char *>(a.dst) + poly * a.poly_bytes;  // zeroed by the caller
   for (uint64_t wd = 0; wd < (degree + 31) / 32; ++wd) {
     uint32_t bits = bitmap[wd];
     while (bits) {
@@ -137,6 +136,49 @@ __global__ void __launch_bounds__(64) hwt_kernel(const SampleArgs a, uint32_t *h
       for (uint32_t cm = 0; cm < a.nmoduli; ++cm)
         store_any(dst, a.limb_bits, (uint64_t)cm * degree + wd * 32 + bit, (a.moduli[cm] - 1) + sign);
     }
+  }
+  return nonce - start_nonce;
+}
+
+__global__ void __launch_bounds__(64) hwt_kernel(const SampleArgs a, uint32_t *hit_all, uint32_t *bitmap_all, uint32_t *used) {
+  const uint64_t degree = 1ull << a.log2_degree;
+  const uint64_t poly = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (poly >= a.batch) return;
+  // bitmap and destination were zeroed by the launcher
+  used[poly] = (uint32_t)hwt_one(a, poly, a.first_nonce + poly * a.param1, hit_all + poly * a.param0, bitmap_all + poly * ((degree + 31) / 32));
+}
+
+// One CTA.  Invariant: the polynomials [done, batch) have been drawn with start nonces start + (i - done) * param1.  Find the
+// first of them that used another number of nonces; everything up to and including it is final, the stream continues right
+// after it, and the polynomials behind it are drawn again from there.  Ends when no polynomial deviates (at once, normally).
+// result[0] = nonces the whole batch consumed.
+__global__ void __launch_bounds__(256) hwt_repair_kernel(const SampleArgs a, uint32_t *hit_all, uint32_t *bitmap_all, uint32_t *used,
+                                                         unsigned long long *result) {
+  __shared__ unsigned int first_bad;
+  const uint64_t degree = 1ull << a.log2_degree, words = (degree + 31) / 32;
+  uint64_t done = 0, start = a.first_nonce;
+  for (;;) {
+    if (threadIdx.x == 0) first_bad = 0xffffffffu;
+    __syncthreads();
+    for (uint64_t i = done + threadIdx.x; i < a.batch; i += blockDim.x)
+      if (used[i] != (uint32_t)a.param1) { atomicMin(&first_bad, (unsigned int)i); break; }
+    __syncthreads();
+    const uint64_t bad = first_bad;
+    __syncthreads();
+    if (bad == 0xffffffffu) {
+      if (threadIdx.x == 0) result[0] = start + (a.batch - done) * a.param1 - a.first_nonce;
+      return;
+    }
+    start += (bad - done) * a.param1 + used[bad];
+    done = bad + 1;
+    for (uint64_t i = done + threadIdx.x; i < a.batch; i += blockDim.x) {
+      uint32_t *bitmap = bitmap_all + i * words;
+      for (uint64_t w = 0; w < words; ++w) bitmap[w] = 0;
+      unsigned char *dst = reinterpret_cast<unsigned char *>(a.dst) + i * a.poly_bytes;
+      for (uint64_t b = 0; b < a.poly_bytes; b += 4) *reinterpret_cast<uint32_t *>(dst + b) = 0;  // core.hpp:383
+      used[i] = (uint32_t)hwt_one(a, i, start + (i - done) * a.param1, hit_all + i * a.param0, bitmap);
+    }
+    __syncthreads();
   }
 }
 
@@ -397,22 +439,29 @@ cudaError_t launch_gaussian(GaussArgs a, int device, int num_sms, cudaStream_t s
   return cudaGetLastError();
 }
 
-cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream, cudaMemPool_t pool) {
+cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream, cudaMemPool_t pool, unsigned long long *result) {
   if (a.batch == 0) return cudaSuccess;
   const uint64_t degree = 1ull << a.log2_degree, hwt = a.param0;
   const size_t hit_bytes = (size_t)a.batch * hwt * 4, bm_bytes = (size_t)a.batch * ((degree + 31) / 32) * 4;
+  const size_t used_bytes = ((size_t)a.batch * 4 + 15) & ~(size_t)15;
   unsigned char *scratch = nullptr;
-  cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), hit_bytes + bm_bytes, pool, stream);
+  cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), hit_bytes + bm_bytes + used_bytes + 16, pool, stream);
   if (e != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(scratch + hit_bytes, 0, bm_bytes, stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(a.dst, 0, (size_t)a.batch * a.poly_bytes, stream)) != cudaSuccess) return e;  // core.hpp:383
-  hwt_kernel<<<(a.batch + 63) / 64, 64, 0, stream>>>(a, reinterpret_cast<uint32_t *>(scratch), reinterpret_cast<uint32_t *>(scratch + hit_bytes));
-  e = cudaGetLastError();
+  uint32_t *hit = reinterpret_cast<uint32_t *>(scratch), *bitmap = reinterpret_cast<uint32_t *>(scratch + hit_bytes);
+  uint32_t *used = reinterpret_cast<uint32_t *>(scratch + hit_bytes + bm_bytes);
+  unsigned long long *res = reinterpret_cast<unsigned long long *>(scratch + hit_bytes + bm_bytes + used_bytes);
+  if ((e = cudaMemsetAsync(bitmap, 0, bm_bytes, stream)) == cudaSuccess &&
+      (e = cudaMemsetAsync(a.dst, 0, (size_t)a.batch * a.poly_bytes, stream)) == cudaSuccess) {  // core.hpp:383
+    hwt_kernel<<<(a.batch + 63) / 64, 64, 0, stream>>>(a, hit, bitmap, used);
+    hwt_repair_kernel<<<1, 256, 0, stream>>>(a, hit, bitmap, used, res);
+    e = cudaGetLastError();
+    if (e == cudaSuccess && result) e = cudaMemcpyAsync(result, res, sizeof(*result), cudaMemcpyDeviceToHost, stream);
+  }
   cudaFreeAsync(scratch, stream);
   return e;
 }
 
-cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream, cudaMemPool_t pool) {
+cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStream_t stream, cudaMemPool_t pool, unsigned long long *hwt_used) {
   const uint64_t total = (uint64_t)a.batch * a.blocks_per_poly;
   if (total == 0) return cudaSuccess;
   uint64_t blocks = (total + 255) / 256;
@@ -421,7 +470,7 @@ cudaError_t launch_sampler(int kind, const SampleArgs &a, int num_sms, cudaStrea
     case SAMPLE_UNIFORM: uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
     case SAMPLE_NON_UNIFORM: non_uniform_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
     case SAMPLE_ZO: zo_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a); break;
-    case SAMPLE_HWT: return launch_hwt(a, stream, pool);
+    case SAMPLE_HWT: return launch_hwt(a, stream, pool, hwt_used);
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();

@@ -102,11 +102,15 @@ class Oracle:
         self.lib().nflo_non_uniform(self.h, out.ctypes.data, batch, upper_bound, amplifier, bytes(key), first_nonce)
         return out
 
-    def hwt(self, batch, hwt, key, first_nonce):
-        """(polys, number of fastrandombytes calls made)"""
+    def hwt(self, batch, hwt, key, first_nonce, test_shrink=0):
+        """(polys, number of fastrandombytes calls made); test_shrink > 0 cuts the top 2^-test_shrink part off the index
+        sampler's acceptance range (forces the extra refills that the real rule makes astronomically rare)"""
         out = np.empty((batch, self.M, self.N), dtype=self.dtype)
         calls = ctypes.c_uint64()
-        rc = self.lib().nflo_hwt(self.h, out.ctypes.data, batch, hwt, bytes(key), first_nonce, ctypes.byref(calls))
+        L = self.lib()
+        L.nflo_hwt_test.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_uint64,
+                                    ctypes.c_uint, ctypes.POINTER(ctypes.c_uint64)]
+        rc = L.nflo_hwt_test(self.h, out.ctypes.data, batch, hwt, bytes(key), first_nonce, test_shrink, ctypes.byref(calls))
         assert rc == 0
         return out, calls.value
 

@@ -370,3 +370,44 @@ def test_baseline_configs_at_full_batch(name, bits, N, M, batch):
     c.free(pa)
     c.free(pf)
     c.close()
+
+
+# ---- hwt sampler: the data-dependent nonce count ---------------------------------------------------------------------------------
+
+def test_oracle_hwt_test_knob_only_changes_the_rejection_rule():
+    o = Oracle(64, 1024, 2)
+    key = bytes(range(32))
+    a, ca = o.hwt(6, 64, key, 5)
+    b, cb = o.hwt(6, 64, key, 5, test_shrink=0)
+    assert ca == cb == 6 * 16 and np.array_equal(a, b)
+    c, cc = o.hwt(64, 64, key, 100, test_shrink=12)   # a rejection costs this shape a whole extra refill: 11 of 64 polys deviate
+    assert cc > 64 * 16
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,N,M,hwt,shrink", [(32, 512, 1, 20, 7), (64, 1024, 2, 64, 12), (64, 256, 1, 16, 8), (64, 1024, 2, 64, 0)])
+def test_hwt_follows_the_reference_nonce_sequence_when_a_draw_needs_an_extra_refill(bits, N, M, hwt, shrink, monkeypatch):
+    """poly::set(hwt_dist) (core.hpp:355-392) refills its index buffer one more time when rejected indices push a polynomial
+    past a refill boundary, which moves the start nonce of every later polynomial.  With the real rejection rule that has
+    probability < 2^-44 per draw, so the test shrinks the acceptance range in the device sampler and in the oracle alike
+    (NFLGPU_HWT_TEST_REJECT_SHIFT / test_shrink): 2, 11 and 36 of 64 polynomials then deviate, and the device must still
+    reproduce the sequential stream — polynomials and nonce count."""
+    if shrink:
+        monkeypatch.setenv("NFLGPU_HWT_TEST_REJECT_SHIFT", str(shrink))
+    else:
+        monkeypatch.delenv("NFLGPU_HWT_TEST_REJECT_SHIFT", raising=False)
+    c, o = nb.Context(bits, N, M), Oracle(bits, N, M)
+    key = bytes(range(32))
+    batch = 64
+    want, calls = o.hwt(batch, hwt, key, 100, test_shrink=shrink)
+    normal = (N - hwt + hwt - 1) // hwt + 1
+    assert (calls != batch * normal) == bool(shrink)
+    p = c.alloc(batch)
+    used = c.hwt_count(p, batch, hwt, key, 100)
+    got = np.empty_like(want)
+    c.download(got, p, batch)
+    c.sync()
+    assert used == calls
+    assert np.array_equal(got, want)
+    c.free(p)
+    c.close()
