@@ -381,13 +381,11 @@ def run_secondary(nb, torch, np, dist, world, rank, local, stream, peak):
             ctx.ntt_fwd(mine, da.data_ptr(), nb_, sh)
             ctx.sync(sh)
             full_ctx = nb.Context(bits, N, M, device=local)
-            slab_ctx = ctx
+            dst, slabs, close_peers = sharding.gather_residues_peer(full_ctx, ctx, mine, shard, world, rank, sh)
+            mapped = slabs[1:]
             handles = [None] * world
-            dist.all_gather_object(handles, (slab_ctx.ipc_export(mine), shard.poly0, shard.npolys, shard.res0, shard.nres))
-            peers = [(r, h) for r, h in enumerate(handles) if r != rank and h[1] == shard.poly0 and h[2] == shard.npolys]
-            mapped = [(full_ctx.ipc_open(h[0]), h[3], h[4]) for _, h in peers]
-            slabs = [(mine, shard.res0, shard.nres)] + mapped
-            dst = full_ctx.alloc(nb_)
+            dist.all_gather_object(handles, (None, shard.poly0, shard.npolys, shard.res0, shard.nres))
+            peers = [(r, handles[r]) for r in sharding.residue_partners([sharding.Shard(*h[1:]) for h in handles], rank)]
             dist.barrier()
             ms_g = timed(lambda: full_ctx.gather_residues(dst, slabs, nb_, sh), iters=10, warm=3)
             full_ctx.gather_residues(dst, slabs, nb_, sh)
@@ -409,8 +407,7 @@ def run_secondary(nb, torch, np, dist, world, rank, local, stream, peak):
                              "how": "nflgpu_ipc_export/open + nflgpu_gather_residues: one strided cudaMemcpy2DAsync per slab, destination "
                                     "[batch][14][4096] written in place; all ranks gather at once; max over ranks"}
             dist.barrier()
-            for m_, _, _ in mapped:
-                full_ctx.ipc_close(m_)
+            close_peers()
             dist.barrier()
             full_ctx.free(dst)
             ctx.free(mine)

@@ -247,6 +247,11 @@ int nflgpu_ipc_open(nflgpu_ctx *ctx, const nflgpu_ipc_handle *handle, void **pee
 int nflgpu_ipc_close(nflgpu_ctx *ctx, void *peer_ptr);
 int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *slabs, const size_t *first_residue,
                            const size_t *nresidues, size_t nslabs, size_t batch, void *stream);
+/* The consumer fused with the gather: nflgpu_poly2mpz reading every residue straight from the slab that holds it (same slab
+ * description as nflgpu_gather_residues; the slabs must cover each residue of the full context exactly once).  Peer slabs are
+ * read over NVLink by the lift kernel itself, coalesced along the coefficient index; no gathered copy is ever written. */
+int nflgpu_poly2mpz_slabs(nflgpu_ctx *ctx, uint64_t *dst_words, const void *const *slabs, const size_t *first_residue,
+                          const size_t *nresidues, size_t nslabs, size_t batch, void *stream);
 
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked

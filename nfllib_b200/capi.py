@@ -84,6 +84,7 @@ def lib():
         L.nflgpu_ipc_open.argtypes = [vp, vp, ctypes.POINTER(vp)]
         L.nflgpu_ipc_close.argtypes = [vp, vp]
         L.nflgpu_gather_residues.argtypes = [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, sz, vp]
+        L.nflgpu_poly2mpz_slabs.argtypes = [vp, vp, ctypes.POINTER(vp), ctypes.POINTER(sz), ctypes.POINTER(sz), sz, sz, vp]
         _lib = L
     return _lib
 
@@ -154,7 +155,11 @@ class Gaussian:
             lib().nflgpu_gaussian_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class Context:
@@ -180,7 +185,11 @@ class Context:
             lib().nflgpu_ctx_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown: the module globals may already be gone
+            pass
 
     def batch_bytes(self, batch):
         return lib().nflgpu_batch_bytes(self.h, batch)
@@ -332,6 +341,14 @@ class Context:
                                     None if ops[0] is None else ops[0].ctypes.data,
                                     None if ops[1] is None else ops[1].ctypes.data, batch))
         return out
+
+    def poly2mpz_slabs(self, dst_words, slabs, batch, stream=0):
+        """nflgpu_poly2mpz_slabs: the CRT lift reading each residue from the slab (local or peer) that holds it."""
+        n = len(slabs)
+        ptrs = (ctypes.c_void_p * n)(*[s[0] for s in slabs])
+        first = (ctypes.c_size_t * n)(*[s[1] for s in slabs])
+        cnt = (ctypes.c_size_t * n)(*[s[2] for s in slabs])
+        _check(lib().nflgpu_poly2mpz_slabs(self.h, dst_words, ptrs, first, cnt, n, batch, stream))
 
     def host_register(self, array):
         """nflgpu_host_register: page-lock a numpy array so that host_op DMAs it directly."""

@@ -598,9 +598,11 @@ int ensure_lift_tables(nflgpu_ctx *ctx) {
   ctx->lift_words = (int)W;
   return NFLGPU_OK;
 }
-int run_lift(nflgpu_ctx *ctx, int dir, void *polys, uint64_t *words, size_t batch, void *stream) {
+int run_lift(nflgpu_ctx *ctx, int dir, void *polys, uint64_t *words, size_t batch, void *stream, const void *const *slabs = nullptr,
+             const size_t *first_residue = nullptr, const size_t *nresidues = nullptr, size_t nslabs = 0) {
   int rc;
-  if ((rc = check_buf(ctx, polys, "polys"))) return rc;
+  if (!slabs && (rc = check_buf(ctx, polys, "polys"))) return rc;
+  if (ctx && ctx->nmoduli > LIFT_MAX_RESIDUES) { set_error("CRT lift supports at most 40 residues"); return NFLGPU_ERR_UNSUPPORTED; }
   if (!words || (reinterpret_cast<uintptr_t>(words) & 7)) { set_error("bad words buffer"); return NFLGPU_ERR_ARG; }
   if (batch > 0xffffffffu) { set_error("batch too large"); return NFLGPU_ERR_ARG; }
   if (batch == 0) return NFLGPU_OK;
@@ -610,6 +612,23 @@ int run_lift(nflgpu_ctx *ctx, int dir, void *polys, uint64_t *words, size_t batc
   const size_t M = ctx->nmoduli, W = ctx->lift_words;
   LiftArgs a;
   a.polys = polys; a.words = words; a.moduli = ctx->d_moduli64; a.consts = ctx->d_consts;
+  const size_t row = ctx->degree * ctx->limb_bytes;
+  if (!slabs) {
+    for (size_t cm = 0; cm < M; ++cm) { a.res_ptr[cm] = static_cast<const char *>(polys) + cm * row; a.res_stride[cm] = M * ctx->degree; }
+  } else {  // residue groups in separate (possibly peer-device) slabs [batch][nres][degree]: every residue exactly once
+    std::vector<int> seen(M, 0);
+    for (size_t k = 0; k < nslabs; ++k) {
+      if ((rc = check_buf(ctx, slabs[k], "slab"))) return rc;
+      if (nresidues[k] == 0 || first_residue[k] + nresidues[k] > M) { set_error("lift: residue range outside the context"); return NFLGPU_ERR_ARG; }
+      for (size_t j = 0; j < nresidues[k]; ++j) {
+        const size_t cm = first_residue[k] + j;
+        a.res_ptr[cm] = static_cast<const char *>(slabs[k]) + j * row;
+        a.res_stride[cm] = nresidues[k] * ctx->degree;
+        ++seen[cm];
+      }
+    }
+    for (size_t cm = 0; cm < M; ++cm) if (seen[cm] != 1) { set_error("lift: the slabs must cover every residue exactly once"); return NFLGPU_ERR_ARG; }
+  }
   a.inv = ctx->d_lift; a.c64 = ctx->d_lift + M; a.qhat = ctx->d_lift + 2 * M; a.q = ctx->d_lift + 2 * M + M * W;
   a.nmoduli = (uint32_t)M; a.log2_degree = (uint32_t)ctx->log2_degree; a.batch = (uint32_t)batch;
   CUDA_TRY(launch_lift(ctx->limb_bits, dir, (int)W, a, ctx->num_sms, (cudaStream_t)stream));
@@ -627,6 +646,11 @@ int nflgpu_lift_words(nflgpu_ctx *ctx, size_t *words_per_coefficient) {
 }
 int nflgpu_poly2mpz(nflgpu_ctx *ctx, uint64_t *dst_words, const void *src_polys, size_t batch, void *stream) {
   return run_lift(ctx, 0, const_cast<void *>(src_polys), dst_words, batch, stream);
+}
+int nflgpu_poly2mpz_slabs(nflgpu_ctx *ctx, uint64_t *dst_words, const void *const *slabs, const size_t *first_residue, const size_t *nresidues,
+                          size_t nslabs, size_t batch, void *stream) {
+  if (!ctx || !slabs || !first_residue || !nresidues || nslabs == 0) { set_error("nflgpu_poly2mpz_slabs: null argument"); return NFLGPU_ERR_ARG; }
+  return run_lift(ctx, 0, nullptr, dst_words, batch, stream, slabs, first_residue, nresidues, nslabs);
 }
 int nflgpu_mpz2poly(nflgpu_ctx *ctx, void *dst_polys, const uint64_t *src_words, size_t batch, void *stream) {
   return run_lift(ctx, 1, dst_polys, const_cast<uint64_t *>(src_words), batch, stream);

@@ -26,13 +26,13 @@ __global__ void __launch_bounds__(128) poly2words_kernel(const LiftArgs a) {
   const uint64_t degree = 1ull << a.log2_degree;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t b = t >> a.log2_degree, i = t & (degree - 1);
-    const Store *src = reinterpret_cast<const Store *>(a.polys) + b * a.nmoduli * degree + i;
     uint64_t acc[W + 1];
 #pragma unroll
     for (int k = 0; k <= W; ++k) acc[k] = 0;
     for (uint32_t cm = 0; cm < a.nmoduli; ++cm) {
       const Word p = (Word)a.moduli[cm];
-      const uint64_t v = PW<LB>::mulmod((Word)src[(uint64_t)cm * degree], (Word)a.inv[cm], p, a.consts[cm]);  // a_cm * Qhat_cm^-1 mod p_cm
+      const Word limb = (Word)__ldg(reinterpret_cast<const Store *>(a.res_ptr[cm]) + b * a.res_stride[cm] + i);
+      const uint64_t v = PW<LB>::mulmod(limb, (Word)a.inv[cm], p, a.consts[cm]);  // a_cm * Qhat_cm^-1 mod p_cm
       const uint64_t *qh = a.qhat + (uint64_t)cm * W;
       uint64_t carry = 0;
 #pragma unroll

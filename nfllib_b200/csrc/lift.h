@@ -6,10 +6,14 @@
 
 namespace nflgpu {
 
-enum { LIFT_MAX_WORDS = 16 };
+enum { LIFT_MAX_WORDS = 16, LIFT_MAX_RESIDUES = 40 };
 
 struct LiftArgs {
-  void *polys;             // limb[batch][nmoduli][degree]
+  void *polys;             // limb[batch][nmoduli][degree] (mpz2poly destination; poly2mpz reads through res_ptr)
+  // poly2mpz: residue cm of polynomial b starts at res_ptr[cm] + b * res_stride[cm] limbs -- one batch buffer, or slabs of
+  // residue groups that may live in the memory of peer devices (read over NVLink by the lift kernel itself)
+  const void *res_ptr[LIFT_MAX_RESIDUES];
+  uint64_t res_stride[LIFT_MAX_RESIDUES];
   uint64_t *words;         // uint64_t[batch][degree][W], little-endian words
   const uint64_t *moduli;  // [nmoduli]
   const uint64_t *consts;  // Barrett constants (pointwise.h)

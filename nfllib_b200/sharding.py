@@ -6,7 +6,12 @@ and a context (`nflgpu_ctx_create(..., first_modulus, ...)`) over just the resid
 needed when a caller wants the complete RNS vector of every polynomial on one device (e.g. before a CRT lift,
 include/nfl/gmp.hpp:183-209): `gather_residues` does that with one all_gather over NCCL (NVLink / NVSwitch).
 
-Host-side logic only (pure Python + torch.distributed); tested on CPU with gloo, world_size 2."""
+`gather_residues_peer` does it without a collective library: every rank exports its slab (CUDA IPC through the C ABI), maps
+its partners' and pulls them over NVLink with one strided copy per slab, straight into [npolys][nmoduli][degree]
+(nflgpu_gather_residues) -- the form a C++ caller of nflgpu_poly2mpz uses.
+
+Host-side logic only (pure Python + torch.distributed for the handle exchange); the partitioning and the exchange protocol
+are tested on CPU with gloo, world_size 2."""
 from dataclasses import dataclass
 
 
@@ -76,3 +81,33 @@ def gather_residues(local, shard, batch, nmoduli, world, group=None):
     for (p0, n, r0, nr), slab in zip(shards, slabs):
         full[p0:p0 + n, r0:r0 + nr, :] = slab[:n * nr * degree].reshape(n, nr, degree)
     return full
+
+
+def residue_partners(shards, rank):
+    """Ranks that hold the OTHER residue ranges of this rank's polynomial range (`shards` = every rank's Shard)."""
+    me = shards[rank]
+    return [r for r, s in enumerate(shards) if r != rank and s.poly0 == me.poly0 and s.npolys == me.npolys]
+
+
+def gather_residues_peer(full_ctx, slab_ctx, slab_ptr, shard, world, rank, stream=0, group=None):
+    """Every residue of this rank's polynomials on this rank's device, through peer memory.
+
+    slab_ptr: this rank's transformed slab [npolys][nres][degree], an allocation of its own made by slab_ctx.alloc() (its CUDA
+    IPC handle must name exactly the slab); full_ctx: a context over all residues on the same device.  Returns
+    (dst pointer from full_ctx.alloc, close) -- call close() once every rank is done reading (it unmaps the peers).
+    The caller has synchronised the stream that produced slab_ptr; the handle exchange below is the cross-rank barrier."""
+    import torch.distributed as dist
+    info = [None] * world
+    dist.all_gather_object(info, (slab_ctx.ipc_export(slab_ptr), shard.poly0, shard.npolys, shard.res0, shard.nres), group=group)
+    shards = [Shard(i[1], i[2], i[3], i[4]) for i in info]
+    mapped = [(full_ctx.ipc_open(info[r][0]), shards[r].res0, shards[r].nres) for r in residue_partners(shards, rank)]
+    slabs = [(slab_ptr, shard.res0, shard.nres)] + mapped
+    covered = sorted((r0, n) for _, r0, n in slabs)
+    assert sum(n for _, n in covered) == full_ctx.nmoduli and covered[0][0] == 0, "residue ranges of the partners do not tile the full context"
+    dst = full_ctx.alloc(shard.npolys)
+    full_ctx.gather_residues(dst, slabs, shard.npolys, stream)
+
+    def close():
+        for p, _, _ in mapped:
+            full_ctx.ipc_close(p)
+    return dst, slabs, close

@@ -254,6 +254,20 @@ def test_gather_residues_from_slab_contexts_equals_the_full_context(bits, N, M, 
     assert np.array_equal(got, want)
     with pytest.raises(nb.NflGpuError):
         full.gather_residues(dst, [(slabs[0][0], M - 1, 2)], batch)   # residue range outside the context
+    # the consumer fused with the gather: the CRT lift (gmp.hpp:183-209) reading each residue from its slab == the lift of the
+    # gathered batch == the big-integer restatement
+    import torch
+    from oracle_lib import crt_lift
+    W = full.lift_words()
+    w1 = torch.zeros((batch, N, W), dtype=torch.int64, device="cuda")
+    w2 = torch.zeros_like(w1)
+    full.poly2mpz_slabs(w1.data_ptr(), slabs, batch)
+    full.poly2mpz(w2.data_ptr(), dst, batch)
+    full.sync()
+    assert torch.equal(w1, w2)
+    assert np.array_equal(w1[:3].cpu().numpy().view(np.uint64), crt_lift(want[:3], [int(p) for p in full.moduli]))
+    with pytest.raises(nb.NflGpuError):
+        full.poly2mpz_slabs(w1.data_ptr(), slabs[:-1], batch)         # a residue is missing
     for cs, (p, _, _) in zip(ctxs, slabs):
         cs.free(p)
         cs.close()
@@ -283,7 +297,14 @@ def _ipc_worker(rank, conn, bits, N, M, batch, ndev):
         got = np.empty_like(a)
         full.download(got, dst, batch)
         full.sync()
-        conn.send(sha(got))
+        import torch
+        W = full.lift_words()
+        words = torch.zeros((batch, N, W), dtype=torch.int64, device=f"cuda:{dev}")
+        lifted = torch.zeros_like(words)
+        full.poly2mpz_slabs(words.data_ptr(), slabs, batch)      # the lift reads the peer's residues through the mapping
+        full.poly2mpz(lifted.data_ptr(), dst, batch)
+        full.sync()
+        conn.send(sha(got) + (":lift-ok" if torch.equal(words, lifted) else ":lift-differs"))
         conn.recv()                                # both have finished reading: safe to unmap and free
         full.ipc_close(peer)
         conn.send("done")
@@ -312,7 +333,7 @@ def test_gather_residues_across_two_processes_over_cuda_ipc():
         for r in range(2):
             pipes[r][0].send("ok")
         a = random_polys(bits, N, M, batch, 4040)
-        want = sha(Oracle(bits, N, M).run("fwd", a))
+        want = sha(Oracle(bits, N, M).run("fwd", a)) + ":lift-ok"
         assert hashes == [want, want], hashes
         assert [pipes[r][0].recv() if pipes[r][0].poll(60) else None for r in range(2)] == ["done", "done"]
     finally:

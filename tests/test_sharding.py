@@ -70,3 +70,81 @@ def test_two_rank_gloo_shard_transform_gather(mode):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_residue_partners_of_config_c4():
+    shards = [sh.shard_residues(8192, 14, 8, r) for r in range(8)]
+    for r in range(8):
+        partners = sh.residue_partners(shards, r)
+        assert len(partners) == 1 and partners[0] == (r ^ 1)  # the rank with the other 7 residues of the same 2048 polynomials
+        assert shards[partners[0]].res0 != shards[r].res0
+
+
+class _FileCtx:
+    """CPU stand-in for nfllib_b200.Context in the peer-gather protocol test: 'device memory' is a file-backed numpy array, an
+    'IPC handle' is its path (padded to 64 bytes), gather_residues is the same strided placement the C ABI does."""
+    registry = {}
+
+    def __init__(self, tmp, N, nmoduli, dtype):
+        self.tmp, self.N, self.nmoduli, self.dtype = tmp, N, nmoduli, dtype
+
+    def alloc(self, batch):
+        path = os.path.join(self.tmp, f"buf_{os.getpid()}_{len(_FileCtx.registry)}.bin")
+        arr = np.lib.format.open_memmap(path, mode="w+", dtype=self.dtype, shape=(batch, self.nmoduli, self.N))
+        _FileCtx.registry[path] = arr
+        return path
+
+    def ipc_export(self, ptr):
+        return ptr.encode().ljust(256, b"\0")
+
+    def ipc_open(self, handle):
+        path = handle.rstrip(b"\0").decode()
+        _FileCtx.registry[path + "#peer"] = np.load(path, mmap_mode="r")
+        return path + "#peer"
+
+    def ipc_close(self, ptr):
+        _FileCtx.registry.pop(ptr)
+
+    def gather_residues(self, dst, slabs, batch, stream=0):
+        out = _FileCtx.registry[dst]
+        for ptr, r0, n in slabs:
+            out[:batch, r0:r0 + n, :] = _FileCtx.registry[ptr][:batch]
+
+
+def _peer_worker(rank, world, port, tmp, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    bits, N, M, batch = 32, 64, 14, 12
+    a = random_polys(bits, N, M, batch, 555)
+    shard = sh.shard_residues(batch, M, world, rank)
+    g = golden_params(bits)
+    sub = {k: (g[k][shard.res0:shard.res0 + shard.nres] if isinstance(g[k], list) else g[k]) for k in g}
+    local = Oracle(bits, N, shard.nres, params=sub).run("fwd", sh.local_view(a, shard))
+    slab_ctx, full_ctx = _FileCtx(tmp, N, shard.nres, np.uint32), _FileCtx(tmp, N, M, np.uint32)
+    mine = slab_ctx.alloc(shard.npolys)
+    _FileCtx.registry[mine][...] = local
+    _FileCtx.registry[mine].flush()
+    dst, slabs, close = sh.gather_residues_peer(full_ctx, slab_ctx, mine, shard, world, rank)
+    exp = Oracle(bits, N, M).run("fwd", a)[shard.poly0:shard.poly0 + shard.npolys]
+    ok = bool(np.array_equal(np.asarray(_FileCtx.registry[dst]), exp)) and len(slabs) == 2
+    dist.barrier()
+    close()
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_peer_gather_protocol(tmp_path):
+    """gather_residues_peer's host logic (handle exchange, partner selection, residue tiling, strided placement) with two gloo
+    ranks and file-backed stand-ins for device memory; the CUDA IPC version of the same exchange runs in tests/test_round2.py."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res) == [(0, True), (1, True)]
