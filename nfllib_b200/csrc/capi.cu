@@ -964,11 +964,12 @@ int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *s
 // ---- host-buffer pipeline ------------------------------------------------------------------------------------
 
 // Staging copies between pageable user memory and the pinned buffers: one host thread moves ~8-10 GB/s, which would cap the
-// pageable path far below PCIe; a few threads on disjoint slices bring it to the DMA rate (NFLGPU_HOST_COPY_THREADS, default 4).
+// pageable path far below PCIe; a few threads on disjoint slices bring it to the DMA rate (NFLGPU_HOST_COPY_THREADS, default min(8, half the host's hardware threads)).
 static void staging_copy(void *dst, const void *src, size_t bytes) {
   static const unsigned want = [] {
     const char *e = std::getenv("NFLGPU_HOST_COPY_THREADS");
-    long v = e ? std::atol(e) : 4;
+    long hw = (long)std::thread::hardware_concurrency() / 2;
+    long v = e ? std::atol(e) : (hw < 2 ? 2 : hw > 8 ? 8 : hw);
     return (unsigned)(v < 1 ? 1 : v > 16 ? 16 : v);
   }();
   const unsigned nt = bytes >= ((size_t)2 << 20) ? want : 1;

@@ -3,6 +3,8 @@
 #define NFLGPU_NTT_LAUNCH_CUH
 #include "ntt_dispatch.h"
 #include "ntt_engine.cuh"
+#include "ntt_cluster.cuh"
+#include <cstdlib>
 
 namespace nflgpu {
 
@@ -20,6 +22,52 @@ template <int LB, int LOGN, int PASS, bool INV> cudaError_t launch_gpasses(NttAr
     return launch_gpasses<LB, LOGN, INV ? PASS - 1 : PASS + 1, INV>(a, last, num_sms, stream);
   } else {
     return cudaSuccess;
+  }
+}
+
+// Cluster path for split transforms with one leading pass (ntt_cluster.cuh).  Returns true when the launch was made (or
+// failed: *err); false when clusters of this shape cannot be scheduled on the device or NFLGPU_NO_CLUSTER=1 asks for the
+// round-1 path (global-memory pass + tile kernel), which stays as the fallback and as the A/B partner.
+template <int LB, int LOGN, int MODE> bool launch_ntt_cluster(const NttLaunch &l, int device, cudaStream_t stream, cudaError_t *err) {
+  typedef ClusterCfg<LB, LOGN> C;
+  if constexpr (!C::OK) {
+    return false;
+  } else {
+    void (*kernel)(const ClusterArgs);
+    if constexpr (MODE == 1) kernel = ntt_cluster_inv_kernel<LB, LOGN>;
+    else if constexpr (MODE == 2) kernel = ntt_cluster_fwd_kernel<LB, LOGN, true>;
+    else kernel = ntt_cluster_fwd_kernel<LB, LOGN, false>;
+    static int max_clusters[64] = {0};  // per device: 0 = not asked yet, -1 = unusable
+    if (device < 0 || device >= 64) return false;
+    static const bool disabled = [] { const char *e = std::getenv("NFLGPU_NO_CLUSTER"); return e && e[0] == '1'; }();
+    if (disabled) return false;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(C::THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream; cfg.attrs = attr; cfg.numAttrs = 1;
+    if (max_clusters[device] == 0) {
+      int n = 0;
+      cfg.gridDim = dim3(C::CL);
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES) != cudaSuccess ||
+          cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        max_clusters[device] = -1;
+      } else {
+        max_clusters[device] = n;
+      }
+    }
+    if (max_clusters[device] < 0) return false;
+    const uint64_t units = (uint64_t)l.batch * l.nmoduli;
+    if (units == 0) { *err = cudaSuccess; return true; }
+    if (units > 0xffffffffull) return false;
+    const uint32_t ncl = (uint32_t)(units < (uint64_t)max_clusters[device] ? units : (uint64_t)max_clusters[device]);
+    ClusterArgs a;
+    a.src = l.src; a.dst = l.dst; a.tw = l.tw; a.moduli = l.moduli; a.nmoduli = l.nmoduli; a.batch = l.batch; a.nclusters = ncl;
+    a.other = l.other; a.consts = l.consts;
+    cfg.gridDim = dim3(ncl * C::CL);
+    *err = cudaLaunchKernelEx(&cfg, kernel, a);
+    return true;
   }
 }
 
@@ -43,6 +91,10 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
     blocks_per_sm[device] = occ > 0 ? occ : 1;
   }
   if (l.batch == 0) return cudaSuccess;
+  if constexpr (C::SPLIT == 1) {  // 64-bit N = 2^15, 2^16: the whole unit on chip in a thread-block cluster
+    cudaError_t ce = cudaSuccess;
+    if (launch_ntt_cluster<LB, LOGN, MODE>(l, device, stream, &ce)) return ce;
+  }
   // the kernels index sub-blocks with 32 bits: larger batches go out as several launches
   constexpr uint32_t kMaxBatch = (1u << 30) >> C::LOGG;
   if (l.batch > kMaxBatch) {

@@ -442,8 +442,8 @@ cudaError_t launch_gaussian(GaussArgs a, int device, int num_sms, cudaStream_t s
 cudaError_t launch_hwt(const SampleArgs &a, cudaStream_t stream, cudaMemPool_t pool, unsigned long long *result) {
   if (a.batch == 0) return cudaSuccess;
   const uint64_t degree = 1ull << a.log2_degree, hwt = a.param0;
-  const size_t hit_bytes = (size_t)a.batch * hwt * 4, bm_bytes = (size_t)a.batch * ((degree + 31) / 32) * 4;
-  const size_t used_bytes = ((size_t)a.batch * 4 + 15) & ~(size_t)15;
+  const size_t hit_bytes = ((size_t)a.batch * hwt * 4 + 15) & ~(size_t)15, bm_bytes = ((size_t)a.batch * ((degree + 31) / 32) * 4 + 15) & ~(size_t)15;
+  const size_t used_bytes = ((size_t)a.batch * 4 + 15) & ~(size_t)15;  // (every part a multiple of 16 bytes: the 8-byte result stays aligned)
   unsigned char *scratch = nullptr;
   cudaError_t e = cudaMallocFromPoolAsync(reinterpret_cast<void **>(&scratch), hit_bytes + bm_bytes + used_bytes + 16, pool, stream);
   if (e != cudaSuccess) return e;

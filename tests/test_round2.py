@@ -432,3 +432,44 @@ def test_hwt_follows_the_reference_nonce_sequence_when_a_draw_needs_an_extra_ref
     assert np.array_equal(got, want)
     c.free(p)
     c.close()
+
+
+# ---- transforms larger than one tile: thread-block clusters ------------------------------------------------------------------------
+
+_SPLIT_SNIPPET = """
+import sys, hashlib, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+import nfllib_b200 as nb
+from oracle_lib import random_polys
+c = nb.Context(64, {N}, {M})
+a = random_polys(64, {N}, {M}, {batch}, 9090)
+f = c.run_device("ntt_fwd", a)
+print(hashlib.sha256(f.tobytes()).hexdigest(), hashlib.sha256(c.run_device("ntt_inv", a).tobytes()).hexdigest())
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,M,batch", [(15, 2, 100), (16, 1, 90)])
+def test_cluster_transforms_with_more_units_than_clusters(n, M, batch):
+    """64-bit N = 2^15 / 2^16 run in clusters of 2 / 4 CTAs with the unit in distributed shared memory (ntt_cluster.cuh); with
+    200 / 90 units the persistent clusters walk several units each.  Against the oracle on a spread of polynomials, the round
+    trip over the whole batch, the fused product, and — whole batch, hash against hash — the round-1 path (global-memory pass +
+    tile kernel), which NFLGPU_NO_CLUSTER=1 selects in a fresh process."""
+    N = 1 << n
+    c, o = nb.Context(64, N, M), Oracle(64, N, M)
+    a = random_polys(64, N, M, batch, 9090)
+    b = random_polys(64, N, M, batch, 9091)
+    fa = c.run_device("ntt_fwd", a)
+    ia = c.run_device("ntt_inv", a)
+    sel = [0, 1, batch // 3, batch // 2, batch - 2, batch - 1]
+    assert np.array_equal(fa[sel], o.run("fwd", a[sel]))
+    assert np.array_equal(ia[sel], o.run("inv", a[sel]))
+    assert np.array_equal(c.run_device("ntt_inv", fa), a)
+    assert np.array_equal(c.run_device("ntt_fwd", a, inplace=True), fa)
+    assert np.array_equal(c.run_device("polymul", a[:8], b[:8]), o.run("polymul", a[:8], b[:8]))
+    env = dict(os.environ, NFLGPU_NO_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", _SPLIT_SNIPPET.format(root=ROOT, tests=os.path.join(ROOT, "tests"), N=N, M=M, batch=batch)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.split() == [sha(fa), sha(ia)]
+    c.close()
