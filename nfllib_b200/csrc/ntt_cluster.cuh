@@ -1,8 +1,9 @@
 // Transforms larger than one shared-memory tile, on chip: a thread-block CLUSTER owns one (residue, polynomial) unit.
 //
-// 64-bit transforms of N = 2^15 (256 KiB per unit) and 2^16 (512 KiB) do not fit the 227 KiB of one SM.  Round 1 ran their
+// 64-bit transforms of N = 2^15 (256 KiB per unit) and above do not fit the 227 KiB of one SM.  Round 1 ran their
 // leading pass as a separate registers <-> HBM kernel (ntt_gpass_kernel): two full HBM round trips per transform.  Here a
-// cluster of CL = 2 / 4 CTAs (sm_100a thread-block clusters, distributed shared memory) keeps the whole unit on chip:
+// cluster of CL CTAs (sm_100a thread-block clusters, distributed shared memory; enabled for the CTA pair of N = 2^15, see
+// ClusterCfg::OK) keeps the whole unit on chip:
 //
 //   forward   pass 0: every thread loads its E coefficients (stride N/E, lane-contiguous) straight from HBM, runs the pass's
 //             butterflies in registers and SCATTERS the results into the sub-block tiles -- register k of a thread belongs to
@@ -38,7 +39,13 @@ template <int LB, int LOGN> struct ClusterCfg : NttCfg<LB, LOGN> {
   static constexpr int THREADS = Base::TPU * TPC;                                                  // = N / (E * CL): also the pass-0 threads per CTA
   static constexpr bool DYNAMIC = false;
   static constexpr size_t SMEM_BYTES = (size_t)TPC * Base::TILE_WORDS * sizeof(Word);
-  static constexpr bool OK = Base::SPLIT == 1 && NSUB % CL == 0 && CL <= 8 && THREADS <= 1024 && THREADS * CL == (Base::N >> Base::e) &&
+  // Measured on B200 (profiles/r02_variants.log): N = 2^15 (2 CTAs x 512 threads, 32 coefficients per thread) 210 / 217 us against
+  // 247 / 257 us for the global-memory pass + tile kernel (M = 2, batch 256); N = 2^16 (4 CTAs x 1024 threads, 16 coefficients) 253 / 267
+  // against 217 / 221 -- four-CTA clusters with two barriers per unit lose, so only the CTA pair is enabled (-DNFLGPU_CLUSTER_MAX=4 to retry).
+#ifndef NFLGPU_CLUSTER_MAX
+#define NFLGPU_CLUSTER_MAX 2
+#endif
+  static constexpr bool OK = Base::SPLIT == 1 && NSUB % CL == 0 && CL <= NFLGPU_CLUSTER_MAX && THREADS <= 1024 && THREADS * CL == (Base::N >> Base::e) &&
                              SMEM_BYTES <= 227 * 1024 && Base::LOGG == Base::e;  // pass 0 runs all e stages: register k <-> sub-block k
 };
 

@@ -78,8 +78,10 @@ template <int LB, int LOGN> struct NttCfg {
 #ifdef NFLGPU_TARGET_THREADS
   static constexpr int TARGET_THREADS = NFLGPU_TARGET_THREADS;
 #else
-  // N = 1024 x 64-bit: one CTA of 1024 threads per SM (16 two-warp units) measured 3.6 % faster than two CTAs of 512 (profiles/r02_variants.log)
-  static constexpr int TARGET_THREADS = (LB == 64 && LOGN == 10) ? 1024 : 256;
+  // N = 1024 x 64-bit: ONE CTA per SM.  Measured (profiles/r02_variants.log): 2 x 512 threads 120.3 / 121.9 us (forward / inverse),
+  // 1 x 1024 threads (64 registers) 115.6 / 117.2, 1 x 896 threads = 14 two-warp units with 72 registers 114.1 / 114.4, 1 x 768 (85
+  // registers) 125.4 / 121.4: the kernel is instruction-issue bound, so seven warps per sub-partition with 2 % fewer instructions win
+  static constexpr int TARGET_THREADS = (LB == 64 && LOGN == 10) ? 896 : 256;
 #endif
   static constexpr int SLOTS = (TPU >= TARGET_THREADS) ? 1 : TARGET_THREADS / TPU;
   static constexpr int THREADS = TPU * SLOTS;

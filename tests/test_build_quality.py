@@ -41,10 +41,11 @@ def test_library_is_built_for_sm_100a_only():
 
 
 def test_headline_kernels_keep_their_occupancy():
-    """64 registers per thread = two 512-thread CTAs per SM = 8 warps per sub-partition; spills stay marginal."""
+    """One 896-thread CTA per SM for N = 1024 x 64-bit = 7 warps per sub-partition: at most 72 registers per thread
+    (65536 / 896 = 73); spills stay marginal."""
     r = resources()
     for k in (FWD10, INV10):
-        assert r[k]["reg"] <= 64, (k, r[k])
+        assert r[k]["reg"] <= 72, (k, r[k])
         assert r[k]["stack"] <= 128, (k, r[k])
     assert r[FWD13]["reg"] <= 128 and r[FWD13]["stack"] <= 256
 

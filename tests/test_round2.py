@@ -449,10 +449,10 @@ print(hashlib.sha256(f.tobytes()).hexdigest(), hashlib.sha256(c.run_device("ntt_
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,M,batch", [(15, 2, 100), (16, 1, 90)])
+@pytest.mark.parametrize("n,M,batch", [(15, 2, 100), (15, 5, 31)])
 def test_cluster_transforms_with_more_units_than_clusters(n, M, batch):
-    """64-bit N = 2^15 / 2^16 run in clusters of 2 / 4 CTAs with the unit in distributed shared memory (ntt_cluster.cuh); with
-    200 / 90 units the persistent clusters walk several units each.  Against the oracle on a spread of polynomials, the round
+    """64-bit N = 2^15 runs in clusters of 2 CTAs with the unit in distributed shared memory (ntt_cluster.cuh); with 200 / 155
+    units the persistent clusters walk several units each.  Against the oracle on a spread of polynomials, the round
     trip over the whole batch, the fused product, and — whole batch, hash against hash — the round-1 path (global-memory pass +
     tile kernel), which NFLGPU_NO_CLUSTER=1 selects in a fresh process."""
     N = 1 << n

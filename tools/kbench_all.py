@@ -16,7 +16,7 @@ if os.environ.get("NFLGPU_LIB"):  # experiment builds (tools/variants.sh): time 
     capi.lib_path = lambda: os.path.abspath(os.environ["NFLGPU_LIB"])
 
 CONFIGS = [("C2", 64, 1024, 4, 4096), ("C3", 64, 16384, 8, 1024), ("C4", 32, 4096, 14, 8192), ("C5", 64, 8192, 6, 2048),
-           ("u64_2k", 64, 2048, 4, 2048), ("u64_4k", 64, 4096, 4, 1024), ("u32_1k", 32, 1024, 8, 8192), ("u32_32k", 32, 32768, 4, 512)]
+           ("u64_2k", 64, 2048, 4, 2048), ("u64_4k", 64, 4096, 4, 1024), ("u64_32k", 64, 32768, 2, 256), ("u32_1k", 32, 1024, 8, 8192), ("u32_32k", 32, 32768, 4, 512)]
 if len(sys.argv) > 1:
     CONFIGS = [c for c in CONFIGS if c[0] in sys.argv[1].split(",")]
 IT = {16: np.int16, 32: np.int32, 64: np.int64}
