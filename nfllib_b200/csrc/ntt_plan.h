@@ -40,7 +40,13 @@ NFLGPU_HD constexpr int plan_emax(int n, int word_bits) {
   return word_bits == 64 ? (n == 10 ? 4 : 5) : (n >= 12 ? 5 : 6);
 }
 NFLGPU_HD constexpr int plan_npass(int n, int word_bits) { return (n + plan_emax(n, word_bits) - 1) / plan_emax(n, word_bits); }
-NFLGPU_HD constexpr int plan_e(int n, int word_bits) { return (n + plan_npass(n, word_bits) - 1) / plan_npass(n, word_bits); }
+NFLGPU_HD constexpr int plan_e(int n, int word_bits) {
+#ifdef NFLGPU_FORCE_E  // experiment builds (one size at a time): e.g. 5 gives N = 4096 the shape (2,5,5) instead of (4,4,4)
+  return NFLGPU_FORCE_E;
+#else
+  return (n + plan_npass(n, word_bits) - 1) / plan_npass(n, word_bits);
+#endif
+}
 // stages in pass i (only the first pass may be short)
 NFLGPU_HD constexpr int plan_r(int n, int word_bits, int i) {
   return i == 0 ? n - plan_e(n, word_bits) * (plan_npass(n, word_bits) - 1) : plan_e(n, word_bits);
