@@ -388,6 +388,7 @@ def run_secondary(nb, torch, np, dist, world, rank, local, stream, peak):
             peers = [(r, handles[r]) for r in sharding.residue_partners([sharding.Shard(*h[1:]) for h in handles], rank)]
             dist.barrier()
             ms_g = timed(lambda: full_ctx.gather_residues(dst, slabs, nb_, sh), iters=10, warm=3)
+            ms_peer = timed(lambda: full_ctx.gather_residues(dst, mapped, nb_, sh), iters=10, warm=2)  # the NVLink part alone
             full_ctx.gather_residues(dst, slabs, nb_, sh)
             full_ctx.sync(sh)
             got = np.empty((nb_, M, N), dtype=dtype)
@@ -401,11 +402,13 @@ def run_secondary(nb, torch, np, dist, world, rank, local, stream, peak):
                 a_sel_full[:, h[3]:h[3] + h[4], :] = ar[sel]
             ok = ok and np.array_equal(got[sel], o.run("fwd", a_sel_full))
             pulled = sum(nb_ * k * N * lb for _, _, k in mapped)
-            rec["gather"] = {"ms": ms_g, "peer_bytes_per_rank": pulled, "peer_gbs_per_rank": pulled / ms_g / 1e6,
-                             "aggregate_peer_gbs": pulled * world / ms_g / 1e6, "nvlink_peak_gbs_per_direction": 900.0,
-                             "frac_of_nvlink": pulled / ms_g / 1e6 / 900.0,
+            rec["gather"] = {"ms": ms_g, "peer_only_ms": ms_peer, "peer_bytes_per_rank": pulled, "peer_gbs_per_rank": pulled / ms_peer / 1e6,
+                             "aggregate_peer_gbs": pulled * world / ms_peer / 1e6, "nvlink_peak_gbs_per_direction": 900.0,
+                             "frac_of_nvlink": pulled / ms_peer / 1e6 / 900.0,
+                             "full_vector_gbs_per_rank": nb_ * M * N * lb / ms_g / 1e6,
                              "how": "nflgpu_ipc_export/open + nflgpu_gather_residues: one strided cudaMemcpy2DAsync per slab, destination "
-                                    "[batch][14][4096] written in place; all ranks gather at once; max over ranks"}
+                                    "[batch][14][4096] written in place, the local slab on a side stream; ms = whole gather, peer_only_ms = the peer slab alone "
+                                    "(what peer_gbs / frac_of_nvlink use); all ranks at once; max over ranks"}
             dist.barrier()
             close_peers()
             dist.barrier()

@@ -83,6 +83,9 @@ struct nflgpu_ctx {
   // stream-ordered scratch (nflgpu_polymul temporaries, sampler scratch, nflgpu_scratch_alloc): a pool owned by the context,
   // destroyed with it, so that cached blocks never outlive the context or touch the application's default pool
   cudaMemPool_t pool = nullptr;
+  // nflgpu_gather_residues: local slabs are placed on a side stream while the caller's stream pulls the peer slabs over NVLink
+  cudaStream_t gather_stream = nullptr;
+  cudaEvent_t gather_fork = nullptr, gather_join = nullptr;
   // dynamic unit scheduling of the NTT kernels (ntt_engine.cuh UnitWalk): one set of nmoduli + 1 device counters per
   // stream, created the first time the stream is seen.  Launches on one stream are ordered and every launch leaves its set
   // zeroed, so a set is never shared by two running kernels.  (A CUDA graph must be replayed on the stream it was captured
@@ -350,6 +353,9 @@ int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
   }
   cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
   for (auto &kv : ctx->sched_by_stream) cudaFree(kv.second);
+  if (ctx->gather_stream) { cudaStreamSynchronize(ctx->gather_stream); cudaStreamDestroy(ctx->gather_stream); }
+  if (ctx->gather_fork) cudaEventDestroy(ctx->gather_fork);
+  if (ctx->gather_join) cudaEventDestroy(ctx->gather_join);
   if (ctx->pool) { cudaDeviceSynchronize(); cudaMemPoolDestroy(ctx->pool); }
   delete ctx;
   return NFLGPU_OK;
@@ -952,11 +958,35 @@ int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *s
   DeviceGuard g(ctx->device);
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
   // one strided DMA per slab: `batch` rows of nres*N limbs, written where they belong in [batch][M][N] (no padded slabs, no
-  // second interleave pass); for a slab in a peer device's memory the copy engine pulls it over NVLink
+  // second interleave pass); for a slab in a peer device's memory the copy engine pulls it over NVLink.  Slabs of this
+  // device go out on a side stream (forked from and joined back into the caller's stream), so the local placement overlaps
+  // the peer transfers instead of queueing behind them.
+  std::vector<char> local(nslabs, 0);
+  size_t nlocal = 0;
+  for (size_t k = 0; k < nslabs; ++k) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, slabs[k]) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device == ctx->device) { local[k] = 1; ++nlocal; }
+    cudaGetLastError();
+  }
+  const bool fork = nlocal > 0 && nlocal < nslabs;
+  if (fork) {
+    if (!ctx->gather_stream) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gather_stream, cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->gather_fork, cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&ctx->gather_join, cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ctx->gather_fork, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx->gather_stream, ctx->gather_fork, 0));
+  }
   for (size_t k = 0; k < nslabs; ++k) {
     const size_t width = nresidues[k] * row;
+    cudaStream_t s = (fork && local[k]) ? ctx->gather_stream : (cudaStream_t)stream;
     CUDA_TRY(cudaMemcpy2DAsync(static_cast<char *>(dst_full) + first_residue[k] * row, full_pitch, slabs[k], width, width, batch,
-                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+                               cudaMemcpyDeviceToDevice, s));
+  }
+  if (fork) {
+    CUDA_TRY(cudaEventRecord(ctx->gather_join, ctx->gather_stream));
+    CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, ctx->gather_join, 0));
   }
   return NFLGPU_OK;
 }

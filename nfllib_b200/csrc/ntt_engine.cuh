@@ -104,6 +104,10 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr bool DYNAMIC = LOGN >= 11 || (LB != 64 && LOGN == 10);
   static constexpr bool CLAIM_LATE = false;
 #endif
+  // A CTA whose twiddles come from global memory (tables too large for shared memory) is not tied to its residue: when the
+  // units of its own residue are exhausted it moves on to the next one.  The grid can then use EVERY SM whatever nmoduli is
+  // (8 moduli used to leave 148 - 8 * 18 = 4 SMs idle), and residues finish together.
+  static constexpr bool HOP = DYNAMIC && !TW_SMEM;
   static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
   static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
@@ -436,11 +440,13 @@ template <class C> struct UnitWalk {
     asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
     return v;
   }
-  __device__ __forceinline__ UnitWalk(const NttArgs &a, unsigned char *smem, int cm, int rank, int slot_, int tl, int lane_base_)
+  __device__ __forceinline__ UnitWalk(const NttArgs &a, unsigned char *smem, int cm, int rank, int slot_, int tl, int lane_base_,
+                                      bool rearm = false)
       : cnt(a.sched + cm), box(reinterpret_cast<uint32_t *>(smem + C::TW_BYTES + 16) + slot_), ahead(0),
         cur((uint32_t)rank * C::SLOTS + slot_), stride(a.ctas_per_residue * C::SLOTS), par(0), slot(slot_), lane_base(lane_base_),
         leader(tl == 0) {
     if (C::DYNAMIC) {
+      if (rearm) unit_sync<C>(slot, lane_base);  // (residue hop) every thread of the slot has read the previous walk's last mailbox word
       if (leader) box[0] = claim(cnt);
       unit_sync<C>(slot, lane_base);
       cur = box[0];
@@ -528,9 +534,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   typedef typename C::TW TW;
   constexpr int S = C::SPLIT;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
-  const TW *tw = stage_twiddles<C>(a, cm, smem);
-  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
+  const int cm0 = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tl & 31);
   Word *tile = reinterpret_cast<Word *>(smem + C::TILE_OFF) + (size_t)slot * C::TILE_WORDS;
@@ -542,7 +546,11 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #ifdef NFLGPU_TRACE
   if (threadIdx.x == 0) atomicMin(&nflgpu_trace_buf[0], trace_now());
 #endif
-  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
+  for (int hop = 0; hop < (C::HOP ? (int)a.nmoduli : 1); ++hop) {  // (HOP: after its own residue the CTA helps with the others)
+  const int cm = cm0 + hop < (int)a.nmoduli ? cm0 + hop : cm0 + hop - (int)a.nmoduli;
+  const TW *tw = stage_twiddles<C>(a, cm, smem);
+  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
+  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base, hop > 0);
   for (; walk.index() < nblocks; walk.advance()) {
     walk.claim_ahead();
     const uint32_t j = walk.index();
@@ -584,6 +592,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #endif
     }
   }
+  }  // hop
 #ifdef NFLGPU_TRACE
   if (tl == 0 && blockIdx.x * C::SLOTS + slot < 8192) nflgpu_trace_buf[1 + blockIdx.x * C::SLOTS + slot] = trace_now();
 #endif
@@ -598,10 +607,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   typedef typename C::TW TW;
   constexpr int S = C::SPLIT;
   extern __shared__ __align__(128) unsigned char smem[];
-  const int cm = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
-  const TW *tw = stage_twiddles<C>(a, cm, smem);
-  const TW ninv = tw[C::N - 1];
-  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
+  const int cm0 = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tl & 31);
   Word *tile = reinterpret_cast<Word *>(smem + C::TILE_OFF) + (size_t)slot * C::TILE_WORDS;
@@ -609,7 +615,12 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
   const uint32_t nblocks = a.batch << C::LOGG;  // the launcher keeps batch << LOGG below 2^31
-  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
+  for (int hop = 0; hop < (C::HOP ? (int)a.nmoduli : 1); ++hop) {
+  const int cm = cm0 + hop < (int)a.nmoduli ? cm0 + hop : cm0 + hop - (int)a.nmoduli;
+  const TW *tw = stage_twiddles<C>(a, cm, smem);
+  const TW ninv = tw[C::N - 1];
+  const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
+  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base, hop > 0);
   for (; walk.index() < nblocks; walk.advance()) {
     walk.claim_ahead();
     const uint32_t j = walk.index();
@@ -636,6 +647,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #pragma unroll
     for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, S>(tid, k)] = (Store)x[k];
   }
+  }  // hop
   UnitWalk<C>::finish(a);
 }
 

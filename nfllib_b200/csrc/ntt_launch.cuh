@@ -125,7 +125,13 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
     if (e != cudaSuccess) return e;
     a.src = a.dst;
   }
-  kernel<<<cpr * l.nmoduli, C::THREADS, C::SMEM_BYTES, stream>>>(a);
+  uint32_t grid = cpr * l.nmoduli;
+  if constexpr (C::HOP) {  // CTAs move from residue to residue: one full wave on every SM, whatever nmoduli is
+    const uint64_t need_all = need * l.nmoduli;
+    grid = need_all < resident ? (uint32_t)need_all : resident;
+    if (grid == 0) grid = 1;
+  }
+  kernel<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if constexpr (C::SPLIT > 0 && MODE == 1) {  // inverse: tile kernel (src -> dst), then global passes SPLIT-1 .. 0 in place
     if (e != cudaSuccess) return e;
