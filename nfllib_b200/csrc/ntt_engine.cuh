@@ -106,8 +106,13 @@ template <int LB, int LOGN> struct NttCfg {
 #endif
   // A CTA whose twiddles come from global memory (tables too large for shared memory) is not tied to its residue: when the
   // units of its own residue are exhausted it moves on to the next one.  The grid can then use EVERY SM whatever nmoduli is
-  // (8 moduli used to leave 148 - 8 * 18 = 4 SMs idle), and residues finish together.
+  // (8 moduli used to leave 148 - 8 * 18 = 4 SMs idle), and residues finish together.  Forward kernels only: measured on B200
+  // (profiles/r02_variants.log) C3 forward 1426.8 -> 1407.8 us; the inverse kernels spill with the extra loop (C5 inverse 915.9 -> 983.6 us).
+#ifdef NFLGPU_NO_HOP
+  static constexpr bool HOP = false;
+#else
   static constexpr bool HOP = DYNAMIC && !TW_SMEM;
+#endif
   static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
   static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
@@ -615,12 +620,11 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
   const uint32_t nblocks = a.batch << C::LOGG;  // the launcher keeps batch << LOGG below 2^31
-  for (int hop = 0; hop < (C::HOP ? (int)a.nmoduli : 1); ++hop) {
-  const int cm = cm0 + hop < (int)a.nmoduli ? cm0 + hop : cm0 + hop - (int)a.nmoduli;
+  const int cm = cm0;  // (the inverse kernels stay bound to their residue: see NttCfg::HOP)
   const TW *tw = stage_twiddles<C>(a, cm, smem);
   const TW ninv = tw[C::N - 1];
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
-  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base, hop > 0);
+  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
   for (; walk.index() < nblocks; walk.advance()) {
     walk.claim_ahead();
     const uint32_t j = walk.index();
@@ -647,7 +651,6 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #pragma unroll
     for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, S>(tid, k)] = (Store)x[k];
   }
-  }  // hop
   UnitWalk<C>::finish(a);
 }
 

@@ -126,7 +126,7 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
     a.src = a.dst;
   }
   uint32_t grid = cpr * l.nmoduli;
-  if constexpr (C::HOP) {  // CTAs move from residue to residue: one full wave on every SM, whatever nmoduli is
+  if constexpr (C::HOP && MODE != 1) {  // forward CTAs move from residue to residue: one full wave on every SM, whatever nmoduli is
     const uint64_t need_all = need * l.nmoduli;
     grid = need_all < resident ? (uint32_t)need_all : resident;
     if (grid == 0) grid = 1;
