@@ -254,13 +254,23 @@ int nflgpu_poly2mpz_slabs(nflgpu_ctx *ctx, uint64_t *dst_words, const void *cons
                           const size_t *nresidues, size_t nslabs, size_t batch, void *stream);
 
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
- * Same operations on HOST buffers: pinned staging, host->device copy, kernel(s), device->host copy, chunked
- * and double-buffered over two streams.  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,
- * 6 sub, 8 polymul, 9 muladd, 10 raw_fwd (core::ntt), 11 raw_inv (core::inv_ntt).  Unused operands are NULL.  These are the calls bench.py's e2e figure times.
- * Not re-entrant per context (the staging buffers belong to the context): serialise calls on one context, or use
+ * Same operations on HOST buffers: host->device copy, kernel(s), device->host copy, cut into chunks that move through a
+ * ring of device buffers on three streams (uploads / kernels / downloads, chained by events), so both PCIe directions
+ * and the kernels overlap.  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,
+ * 6 sub, 8 polymul, 9 muladd, 10 raw_fwd (core::ntt), 11 raw_inv (core::inv_ntt).  Unused operands are NULL.  dst may be
+ * one of the operands (in place).  These are the calls bench.py's e2e figure times.
+ * Not re-entrant per context (the ring belongs to the context): serialise calls on one context, or use
  * one context per host thread. */
 int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host,
                    const void *c_host, size_t batch);
+/* The same call without the final wait: it returns once the last chunk has been queued (it only blocks while the ring is
+ * full), so a caller that streams several independent batches keeps the uploads of the next call running under the
+ * downloads of this one.  Operands and destination must stay valid and untouched until nflgpu_host_sync (or any
+ * nflgpu_host_op on the same context) has returned; only then is dst complete.  An error reported by a later call or by
+ * nflgpu_host_sync may belong to an earlier asynchronous call. */
+int nflgpu_host_op_async(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host,
+                         const void *c_host, size_t batch);
+int nflgpu_host_sync(nflgpu_ctx *ctx);
 /* Pageable host arrays (e.g. posix_memalign'ed nfl::poly[], tests/tools.h:6-17) go through pinned staging buffers with an extra
  * host copy each way (a few host threads, NFLGPU_HOST_COPY_THREADS).  A caller that keeps its arrays can page-lock them once
  * instead — nflgpu_host_register is cudaHostRegister without the CUDA headers — after which nflgpu_host_op DMAs them directly,

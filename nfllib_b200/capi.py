@@ -55,6 +55,8 @@ def lib():
             getattr(L, name).argtypes = [vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_muladd_shoup.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp]
         L.nflgpu_host_op.argtypes = [vp, ci, vp, vp, vp, vp, sz]
+        L.nflgpu_host_op_async.argtypes = [vp, ci, vp, vp, vp, vp, sz]
+        L.nflgpu_host_sync.argtypes = [vp]
         L.nflgpu_uniform.argtypes = [vp, vp, sz, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_non_uniform.argtypes = [vp, vp, sz, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint64, vp]
         L.nflgpu_zo.argtypes = [vp, vp, sz, ctypes.c_uint8, ctypes.c_char_p, ctypes.c_uint64, vp]
@@ -331,16 +333,29 @@ class Context:
         _check(lib().nflgpu_gather_residues(self.h, dst_full, ptrs, first, cnt, n, batch, stream))
 
     # ---- host-buffer call (numpy in, numpy out): H2D + kernel(s) + D2H inside the library ----
-    def host_op(self, op, a, b=None, c=None, out=None):
+    def host_op(self, op, a, b=None, c=None, out=None, wait=True):
+        """nflgpu_host_op; wait=False -> nflgpu_host_op_async (operands and `out` must stay alive and untouched until host_sync())."""
         a = np.ascontiguousarray(a, dtype=self.dtype)
         batch = a.size // (self.degree * self.nmoduli)
         if out is None:
             out = np.empty_like(a)
         ops = [None if x is None else np.ascontiguousarray(x, dtype=self.dtype) for x in (b, c)]
-        _check(lib().nflgpu_host_op(self.h, HOST_OPS[op], out.ctypes.data, a.ctypes.data,
-                                    None if ops[0] is None else ops[0].ctypes.data,
-                                    None if ops[1] is None else ops[1].ctypes.data, batch))
+        fn = lib().nflgpu_host_op if wait else lib().nflgpu_host_op_async
+        if not wait:
+            self._inflight = getattr(self, "_inflight", []) + [(a, ops, out)]  # keep the arrays alive until host_sync
+        _check(fn(self.h, HOST_OPS[op], out.ctypes.data, a.ctypes.data,
+                  None if ops[0] is None else ops[0].ctypes.data,
+                  None if ops[1] is None else ops[1].ctypes.data, batch))
+        if wait:
+            self._inflight = []
         return out
+
+    def host_sync(self):
+        """nflgpu_host_sync: every earlier host_op(..., wait=False) is complete when this returns."""
+        try:
+            _check(lib().nflgpu_host_sync(self.h))
+        finally:
+            self._inflight = []
 
     def poly2mpz_slabs(self, dst_words, slabs, batch, stream=0):
         """nflgpu_poly2mpz_slabs: the CRT lift reading each residue from the slab (local or peer) that holds it."""

@@ -56,11 +56,25 @@ using namespace nflgpu;
     }                                                                                                    \
   } while (0)
 
-struct HostStage {  // one slot of the host-buffer pipeline
-  cudaStream_t stream = nullptr;
+// Host-buffer pipeline (nflgpu_host_op / nflgpu_host_op_async): a ring of chunk slots fed by THREE streams -- every host->device
+// copy goes out on `in`, every kernel on `run`, every device->host copy on `out`, chained per slot by events -- so that each
+// copy engine sees one back-to-back queue (no idle gap while a per-chunk stream switches from its upload to its kernel to its
+// download) and consecutive calls keep both PCIe directions busy across the call boundary.
+struct HostSlot {
   void *dev[4] = {nullptr, nullptr, nullptr, nullptr};   // a, b, c, out
   void *pin[4] = {nullptr, nullptr, nullptr, nullptr};   // pinned staging (only used for pageable user buffers)
-  size_t polys = 0;
+  cudaEvent_t up = nullptr, done = nullptr, down = nullptr;  // uploads finished / kernels finished / download finished
+  bool busy = false;        // `down` has been recorded and not yet waited for
+  void *unstage_to = nullptr;  // pageable destination of this slot's result (copied out of pin[3] when the slot retires)
+  size_t unstage_bytes = 0;
+};
+struct HostPipe {
+  static constexpr int kMaxRing = 16;
+  cudaStream_t in = nullptr, run = nullptr, out = nullptr;
+  HostSlot slot[kMaxRing];
+  int ring = 0;            // slots in use (fixed at the first call: NFLGPU_HOST_RING, default 8)
+  size_t slot_bytes = 0;   // capacity of every device / pinned buffer of a slot
+  unsigned next = 0;       // next slot to use (slots retire in the order they were filled)
 };
 
 struct nflgpu_ctx {
@@ -92,11 +106,9 @@ struct nflgpu_ctx {
   // from, after one eager call on that stream has created the set.)
   std::mutex sched_mu;
   std::unordered_map<void *, uint32_t *> sched_by_stream;
-  static constexpr int kStages = 4;
-  HostStage stage[kStages];
-  size_t stage_polys = 0;  // capacity of every staging buffer, in polynomials
-  // The host-buffer pipeline below uses per-context staging state: concurrent nflgpu_host_op calls on ONE context
+  // The host-buffer pipeline uses per-context staging state: concurrent nflgpu_host_op calls on ONE context
   // must be serialised by the caller (distinct contexts are independent).
+  HostPipe pipe;
 };
 
 namespace {
@@ -346,11 +358,12 @@ int nflgpu_ctx_create(nflgpu_ctx **out, int limb_bits, size_t degree, size_t nmo
 int nflgpu_ctx_destroy(nflgpu_ctx *ctx) {
   if (!ctx) return NFLGPU_OK;
   DeviceGuard g(ctx->device);
-  for (auto &s : ctx->stage) {
-    if (s.stream) cudaStreamSynchronize(s.stream);
+  for (cudaStream_t st : {ctx->pipe.in, ctx->pipe.run, ctx->pipe.out}) if (st) cudaStreamSynchronize(st);
+  for (auto &s : ctx->pipe.slot) {
     for (int i = 0; i < 4; ++i) { if (s.dev[i]) cudaFree(s.dev[i]); if (s.pin[i]) cudaFreeHost(s.pin[i]); }
-    if (s.stream) cudaStreamDestroy(s.stream);
+    for (cudaEvent_t ev : {s.up, s.done, s.down}) if (ev) cudaEventDestroy(ev);
   }
+  for (cudaStream_t st : {ctx->pipe.in, ctx->pipe.run, ctx->pipe.out}) if (st) cudaStreamDestroy(st);
   cudaFree(ctx->d_tw_fwd); cudaFree(ctx->d_tw_inv); cudaFree(ctx->d_tw_raw_fwd); cudaFree(ctx->d_tw_raw_inv); cudaFree(ctx->d_lift); cudaFree(ctx->d_moduli_word); cudaFree(ctx->d_moduli64); cudaFree(ctx->d_consts);
   for (auto &kv : ctx->sched_by_stream) cudaFree(kv.second);
   if (ctx->gather_stream) { cudaStreamSynchronize(ctx->gather_stream); cudaStreamDestroy(ctx->gather_stream); }
@@ -1037,7 +1050,64 @@ static bool is_pinned(const void *p) {
   return at.type == cudaMemoryTypeHost;
 }
 
-int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host, const void *c_host, size_t batch) {
+namespace {
+
+int host_dispatch(nflgpu_ctx *ctx, int op, void *const d[4], size_t cnt, void *st) {
+  switch (op) {
+    case 0: return nflgpu_ntt_fwd(ctx, d[3], d[0], cnt, st);
+    case 1: return nflgpu_ntt_inv(ctx, d[3], d[0], cnt, st);
+    case 2: return nflgpu_mul(ctx, d[3], d[0], d[1], cnt, st);
+    case 3: return nflgpu_mul_shoup(ctx, d[3], d[0], d[1], d[2], cnt, st);
+    case 4: return nflgpu_compute_shoup(ctx, d[3], d[0], cnt, st);
+    case 5: return nflgpu_add(ctx, d[3], d[0], d[1], cnt, st);
+    case 6: return nflgpu_sub(ctx, d[3], d[0], d[1], cnt, st);
+    case 8: return nflgpu_polymul(ctx, d[3], d[0], d[1], cnt, st);
+    case 9: return nflgpu_muladd(ctx, d[3], d[0], d[1], d[2], cnt, st);
+    case 10: return nflgpu_ntt_raw_fwd(ctx, d[3], d[0], cnt, st);
+    case 11: return nflgpu_ntt_raw_inv(ctx, d[3], d[0], cnt, st);
+  }
+  set_error("unknown op");
+  return NFLGPU_ERR_ARG;
+}
+
+// waits for the slot's download; a result staged for a pageable destination is handed over now
+int host_retire(HostSlot &s) {
+  if (!s.busy) return NFLGPU_OK;
+  s.busy = false;
+  void *to = s.unstage_to;
+  s.unstage_to = nullptr;
+  CUDA_TRY(cudaEventSynchronize(s.down));
+  if (to) staging_copy(to, s.pin[3], s.unstage_bytes);
+  return NFLGPU_OK;
+}
+
+// retires every slot, oldest first
+int host_drain(nflgpu_ctx *ctx) {
+  HostPipe &p = ctx->pipe;
+  int rc = NFLGPU_OK;
+  for (int i = 0; i < p.ring; ++i) {
+    const int r = host_retire(p.slot[(p.next + i) % p.ring]);
+    if (r != NFLGPU_OK && rc == NFLGPU_OK) rc = r;
+  }
+  return rc;
+}
+
+// after a failure: nothing of the pipeline may still be touching the caller's buffers or the staging memory
+void host_abort(nflgpu_ctx *ctx) {
+  HostPipe &p = ctx->pipe;
+  for (cudaStream_t st : {p.in, p.run, p.out}) if (st) cudaStreamSynchronize(st);
+  for (auto &s : p.slot) { s.busy = false; s.unstage_to = nullptr; }
+}
+
+long env_long(const char *name, long lo, long hi, long dflt) {
+  const char *e = std::getenv(name);
+  if (!e) return dflt;
+  const long v = std::atol(e);
+  return v < lo || v > hi ? dflt : v;
+}
+
+int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host, const void *c_host, size_t batch,
+                  bool wait) {
   if (!ctx || !dst_host || !a_host) { set_error("null argument"); return NFLGPU_ERR_ARG; }
   int nin;
   switch (op) {
@@ -1048,128 +1118,157 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
   }
   const void *in[3] = {a_host, b_host, c_host};
   for (int i = 0; i < nin; ++i) if (!in[i]) { set_error("missing operand"); return NFLGPU_ERR_ARG; }
-  if (batch == 0) return NFLGPU_OK;
   DeviceGuard g(ctx->device);
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
-
+  HostPipe &p = ctx->pipe;
+  if (batch == 0) return wait ? host_drain(ctx) : NFLGPU_OK;
+  if (!p.run) {
+    for (cudaStream_t *st : {&p.in, &p.run, &p.out}) CUDA_TRY(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+  }
   const size_t poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
+  bool pinned[4] = {is_pinned(a_host), nin >= 2 && is_pinned(b_host), nin >= 3 && is_pinned(c_host), is_pinned(dst_host)};
 
   // Optional zero-copy path (NFLGPU_HOST_ZEROCOPY=1): when every operand lives in pinned (device-mapped, UVA) host
   // memory the kernels read and write it directly over PCIe — no staging buffers.  Measured on B200 / PCIe gen5 it
-  // moves 37 GB/s each way against 41 GB/s for the staged pipeline below (tools/e2e_sweep.py), so it is off by default.
+  // moves 37 GB/s each way against 41 GB/s for the staged pipeline (profiles/r01e_variants.log), so it is off by default.
   {
-    const char *zc = std::getenv("NFLGPU_HOST_ZEROCOPY");
-    bool all_pinned = is_pinned(dst_host);
-    for (int i = 0; i < nin; ++i) all_pinned = all_pinned && is_pinned(in[i]);
-    if (all_pinned && zc && zc[0] == '1') {
+    static const bool zc = env_long("NFLGPU_HOST_ZEROCOPY", 0, 1, 0) == 1;
+    bool all_pinned = pinned[3];
+    for (int i = 0; i < nin; ++i) all_pinned = all_pinned && pinned[i];
+    if (all_pinned && zc) {
       void *dp[4] = {nullptr, nullptr, nullptr, nullptr};
       const void *hp[4] = {a_host, b_host, c_host, dst_host};
       for (int i = 0; i < 4; ++i)
         if (hp[i]) CUDA_TRY(cudaHostGetDevicePointer(&dp[i], const_cast<void *>(hp[i]), 0));
-      if (!ctx->stage[0].stream) CUDA_TRY(cudaStreamCreateWithFlags(&ctx->stage[0].stream, cudaStreamNonBlocking));
-      void *st = ctx->stage[0].stream;
-      int rc = NFLGPU_OK;
-      switch (op) {
-        case 0: rc = nflgpu_ntt_fwd(ctx, dp[3], dp[0], batch, st); break;
-        case 1: rc = nflgpu_ntt_inv(ctx, dp[3], dp[0], batch, st); break;
-        case 2: rc = nflgpu_mul(ctx, dp[3], dp[0], dp[1], batch, st); break;
-        case 3: rc = nflgpu_mul_shoup(ctx, dp[3], dp[0], dp[1], dp[2], batch, st); break;
-        case 4: rc = nflgpu_compute_shoup(ctx, dp[3], dp[0], batch, st); break;
-        case 5: rc = nflgpu_add(ctx, dp[3], dp[0], dp[1], batch, st); break;
-        case 6: rc = nflgpu_sub(ctx, dp[3], dp[0], dp[1], batch, st); break;
-        case 8: rc = nflgpu_polymul(ctx, dp[3], dp[0], dp[1], batch, st); break;
-        case 9: rc = nflgpu_muladd(ctx, dp[3], dp[0], dp[1], dp[2], batch, st); break;
-        case 10: rc = nflgpu_ntt_raw_fwd(ctx, dp[3], dp[0], batch, st); break;
-        case 11: rc = nflgpu_ntt_raw_inv(ctx, dp[3], dp[0], batch, st); break;
-      }
+      const int rc = host_dispatch(ctx, op, dp, batch, p.run);
       if (rc != NFLGPU_OK) return rc;
-      CUDA_TRY(cudaStreamSynchronize(ctx->stage[0].stream));
+      CUDA_TRY(cudaStreamSynchronize(p.run));
       return NFLGPU_OK;
     }
   }
-  // chunk: ~16 MiB per operand (best of a 1..64 MiB sweep on B200 / PCIe gen5, tools/e2e_sweep.py), at least one polynomial; kStages chunks in flight (H2D / kernel / D2H overlap)
-  size_t chunk_bytes = 16u << 20;
-  if (const char *env = std::getenv("NFLGPU_HOST_CHUNK_MIB")) {  // tuning knob
-    const long v = std::atol(env);
-    if (v > 0 && v <= 1024) chunk_bytes = (size_t)v << 20;
-  }
+
+  // Chunk size and ring depth, measured on B200 / PCIe gen5 (profiles/r02_variants.log, block "host pipeline"): copies of 8 MiB
+  // and more run at the rate of whole-array copies (48 GB/s each way at once), smaller ones lose 8-35 %; the ring only has to
+  // cover upload + kernel + download of one chunk.  The first and last chunks of a call are shorter (C/8, C/8, C/4, C/2, C ... C,
+  // C/2, C/4, C/8, C/8): nothing overlaps the first upload and the last download, so they should be small.
+  static const size_t chunk_bytes = (size_t)env_long("NFLGPU_HOST_CHUNK_MIB", 1, 1024, 16) << 20;
+  static const int ring_want = (int)env_long("NFLGPU_HOST_RING", 2, HostPipe::kMaxRing, 4);
+  static const bool ramp = env_long("NFLGPU_HOST_RAMP", 0, 1, 1) == 1;
   size_t chunk = chunk_bytes / poly_bytes;
   if (chunk == 0) chunk = 1;
   if (chunk > batch) chunk = batch;
-  if (ctx->stage_polys < chunk) {  // staging buffers only ever grow (capacity = largest chunk seen so far)
-    ctx->stage_polys = 0;  // a failure below leaves "no staging buffers": the next call allocates all of them again
-    for (auto &s : ctx->stage) {
-      if (!s.stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+  if (p.slot_bytes < chunk * poly_bytes || p.ring == 0) {  // (re)build the ring; buffers only ever grow
+    int rc = host_drain(ctx);
+    if (rc != NFLGPU_OK) { host_abort(ctx); return rc; }
+    for (cudaStream_t st : {p.in, p.run, p.out}) CUDA_TRY(cudaStreamSynchronize(st));
+    p.slot_bytes = 0;  // a failure below leaves "no ring": the next call builds all of it again
+    p.ring = 0;
+    for (int k = 0; k < ring_want; ++k) {
+      HostSlot &s = p.slot[k];
       for (int i = 0; i < 4; ++i) {
         if (s.dev[i]) { void *old = s.dev[i]; s.dev[i] = nullptr; CUDA_TRY(cudaFree(old)); }
         if (s.pin[i]) { void *old = s.pin[i]; s.pin[i] = nullptr; CUDA_TRY(cudaFreeHost(old)); }
         CUDA_TRY(cudaMalloc(&s.dev[i], chunk * poly_bytes));
       }
+      for (cudaEvent_t *ev : {&s.up, &s.done, &s.down})
+        if (!*ev) CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     }
-    ctx->stage_polys = chunk;
+    p.slot_bytes = chunk * poly_bytes;
+    p.ring = ring_want;
+    p.next = 0;
   }
-  // any failure inside the pipeline drains every stage stream before returning: asynchronous copies still target the
-  // caller's buffers and the pinned staging
+
 #define PIPE_TRY(expr)                                                                                   \
   do {                                                                                                   \
     cudaError_t e_ = (expr);                                                                             \
     if (e_ != cudaSuccess) {                                                                             \
       set_error(std::string(#expr) + ": " + cudaGetErrorName(e_) + " (" + cudaGetErrorString(e_) + ")"); \
-      rc = NFLGPU_ERR_CUDA;                                                                              \
-      goto drain;                                                                                        \
+      host_abort(ctx);                                                                                   \
+      return NFLGPU_ERR_CUDA;                                                                            \
     }                                                                                                    \
   } while (0)
-  bool pinned[4] = {is_pinned(a_host), nin >= 2 && is_pinned(b_host), nin >= 3 && is_pinned(c_host), is_pinned(dst_host)};
-  constexpr int NS = nflgpu_ctx::kStages;
-  struct Pending { size_t first, count; bool active; } pend[NS] = {};
-  int rc = NFLGPU_OK;
-  size_t done = 0;
-  auto any_pending = [&]() { for (int i = 0; i < NS; ++i) if (pend[i].active) return true; return false; };
-  for (int k = 0; done < batch || any_pending(); k = (k + 1) % NS) {
-    HostStage &s = ctx->stage[k];
-    if (pend[k].active) {  // retire the chunk that used this stage kStages steps ago
-      PIPE_TRY(cudaStreamSynchronize(s.stream));
-      if (!pinned[3]) staging_copy(static_cast<char *>(dst_host) + pend[k].first * poly_bytes, s.pin[3], pend[k].count * poly_bytes);
-      pend[k].active = false;
+  // a call that fits one chunk has nothing to overlap: all three steps go on one stream (no event hops on the latency path)
+  const bool single = batch <= chunk;
+  cudaStream_t sin = single ? p.run : p.in, sout = single ? p.run : p.out;
+  // ramp: chunk sizes C/8, C/8, C/4, C/2 at both ends of a call that is long enough to have a middle
+  size_t steps[4] = {chunk / 8, chunk / 8, chunk / 4, chunk / 2}, ramp_total = 0;
+  for (size_t &v : steps) { if (v == 0) v = 1; ramp_total += v; }
+  const bool ramped = ramp && batch >= 2 * ramp_total + chunk;
+  int head = 0, tail = 0;
+  for (size_t done = 0; done < batch;) {
+    HostSlot &s = p.slot[p.next];
+    int rc = host_retire(s);  // the chunk that used this slot `ring` chunks ago
+    if (rc != NFLGPU_OK) { host_abort(ctx); return rc; }
+    size_t cnt = (batch - done < chunk) ? batch - done : chunk;
+    if (ramped) {
+      const size_t left = batch - done;
+      if (head < 4) cnt = steps[head++];
+      else if (left > ramp_total) cnt = left - ramp_total < chunk ? left - ramp_total : chunk;  // the middle ends where the tail begins
+      else cnt = steps[3 - tail++];
     }
-    if (done >= batch) continue;
-    const size_t cnt = (batch - done < chunk) ? batch - done : chunk;
+    const size_t bytes = cnt * poly_bytes;
     for (int i = 0; i < nin; ++i) {
       const char *src = static_cast<const char *>(in[i]) + done * poly_bytes;
       if (!pinned[i]) {
-        if (!s.pin[i]) PIPE_TRY(cudaHostAlloc(&s.pin[i], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
-        staging_copy(s.pin[i], src, cnt * poly_bytes);
+        if (!s.pin[i]) PIPE_TRY(cudaHostAlloc(&s.pin[i], p.slot_bytes, cudaHostAllocDefault));
+        staging_copy(s.pin[i], src, bytes);
         src = static_cast<const char *>(s.pin[i]);
       }
-      PIPE_TRY(cudaMemcpyAsync(s.dev[i], src, cnt * poly_bytes, cudaMemcpyHostToDevice, s.stream));
+      PIPE_TRY(cudaMemcpyAsync(s.dev[i], src, bytes, cudaMemcpyHostToDevice, sin));
     }
-    void *st = s.stream;
-    switch (op) {
-      case 0: rc = nflgpu_ntt_fwd(ctx, s.dev[3], s.dev[0], cnt, st); break;
-      case 1: rc = nflgpu_ntt_inv(ctx, s.dev[3], s.dev[0], cnt, st); break;
-      case 2: rc = nflgpu_mul(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
-      case 3: rc = nflgpu_mul_shoup(ctx, s.dev[3], s.dev[0], s.dev[1], s.dev[2], cnt, st); break;
-      case 4: rc = nflgpu_compute_shoup(ctx, s.dev[3], s.dev[0], cnt, st); break;
-      case 5: rc = nflgpu_add(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
-      case 6: rc = nflgpu_sub(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
-      case 8: rc = nflgpu_polymul(ctx, s.dev[3], s.dev[0], s.dev[1], cnt, st); break;
-      case 9: rc = nflgpu_muladd(ctx, s.dev[3], s.dev[0], s.dev[1], s.dev[2], cnt, st); break;
-      case 10: rc = nflgpu_ntt_raw_fwd(ctx, s.dev[3], s.dev[0], cnt, st); break;
-      case 11: rc = nflgpu_ntt_raw_inv(ctx, s.dev[3], s.dev[0], cnt, st); break;
+    if (!single) {
+      PIPE_TRY(cudaEventRecord(s.up, sin));
+      PIPE_TRY(cudaStreamWaitEvent(p.run, s.up, 0));
     }
-    if (rc != NFLGPU_OK) goto drain;
-    char *out = static_cast<char *>(dst_host) + done * poly_bytes;
+#ifdef NFLGPU_HOST_NOKERNEL  // timing experiment (tools/e2e_sweep.py): copies and events only, results are wrong
+    rc = NFLGPU_OK;
+#else
+    rc = host_dispatch(ctx, op, s.dev, cnt, p.run);
+#endif
+    if (rc != NFLGPU_OK) { host_abort(ctx); return rc; }
+    if (!single) {
+      PIPE_TRY(cudaEventRecord(s.done, p.run));
+      PIPE_TRY(cudaStreamWaitEvent(sout, s.done, 0));
+    }
+    char *user = static_cast<char *>(dst_host) + done * poly_bytes, *out = user;
     if (!pinned[3]) {
-      if (!s.pin[3]) PIPE_TRY(cudaHostAlloc(&s.pin[3], ctx->stage_polys * poly_bytes, cudaHostAllocDefault));
+      if (!s.pin[3]) PIPE_TRY(cudaHostAlloc(&s.pin[3], p.slot_bytes, cudaHostAllocDefault));
       out = static_cast<char *>(s.pin[3]);
     }
-    PIPE_TRY(cudaMemcpyAsync(out, s.dev[3], cnt * poly_bytes, cudaMemcpyDeviceToHost, s.stream));
-    pend[k] = {done, cnt, true};
+    PIPE_TRY(cudaMemcpyAsync(out, s.dev[3], bytes, cudaMemcpyDeviceToHost, sout));
+    PIPE_TRY(cudaEventRecord(s.down, sout));
+    s.busy = true;
+    s.unstage_to = pinned[3] ? nullptr : user;
+    s.unstage_bytes = bytes;
+    p.next = (p.next + 1) % (unsigned)p.ring;
     done += cnt;
   }
-drain:
 #undef PIPE_TRY
-  if (rc != NFLGPU_OK) for (auto &s : ctx->stage) if (s.stream) cudaStreamSynchronize(s.stream);
+  if (wait) {
+    const int rc = host_drain(ctx);
+    if (rc != NFLGPU_OK) host_abort(ctx);
+    return rc;
+  }
+  return NFLGPU_OK;
+}
+
+}  // namespace
+
+int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host, const void *c_host, size_t batch) {
+  return host_pipeline(ctx, op, dst_host, a_host, b_host, c_host, batch, true);
+}
+
+int nflgpu_host_op_async(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host, const void *c_host,
+                         size_t batch) {
+  return host_pipeline(ctx, op, dst_host, a_host, b_host, c_host, batch, false);
+}
+
+int nflgpu_host_sync(nflgpu_ctx *ctx) {
+  if (!ctx) { set_error("null context"); return NFLGPU_ERR_ARG; }
+  DeviceGuard g(ctx->device);
+  if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
+  const int rc = host_drain(ctx);
+  if (rc != NFLGPU_OK) host_abort(ctx);
   return rc;
 }
 

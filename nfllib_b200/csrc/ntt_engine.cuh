@@ -73,7 +73,16 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr int VEC = 16 / (int)sizeof(Word);    // words per 16-byte shared-memory vector
   static constexpr int PADW = VEC;                       // 16 bytes of padding per row of E words
   static constexpr int ROW = E + PADW;
-  static constexpr int TILE_WORDS = (NP - SPLIT > 1) ? (B >> e) * ROW : 0;
+  // 32-bit words, N = 4096, shape (4,4,4): rows of 16 words + 16 bytes make the lane-contiguous accesses of passes 0 and 1 and the
+  // 16-byte copies two wavefronts instead of one (tools/bank_conflicts.py; ncu counted 16 M conflicts per launch of the C4 shape).
+  // This shape uses an unpadded tile with an XOR swizzle instead: address bits 2,3 ^= position bits 5,6 and bit 4 ^= bit 8, which
+  // is conflict free for every pass and keeps 16-byte vectors contiguous (swz / swz_k below).
+#ifdef NFLGPU_NO_SWIZZLE
+  static constexpr bool SWZ = false;
+#else
+  static constexpr bool SWZ = WB == 32 && n == 12 && e == 4 && SPLIT == 0;
+#endif
+  static constexpr int TILE_WORDS = (NP - SPLIT > 1) ? (SWZ ? B : (B >> e) * ROW) : 0;
   // CTA size: 256 threads (2+ CTAs per SM)
 #ifdef NFLGPU_TARGET_THREADS
   static constexpr int TARGET_THREADS = NFLGPU_TARGET_THREADS;
@@ -120,6 +129,11 @@ template <int LB, int LOGN> struct NttCfg {
   static NFLGPU_DEVFN int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
   // the same for a compile-time position offset made of register-index bits only (below B by construction)
   static __host__ __device__ constexpr int pad_k(int off) { return off + (off >> e) * PADW; }
+  // XOR-swizzled tile (SWZ): the swizzle term of a position, and the tile address of a position
+  static __host__ __device__ constexpr int swz_x(int pos) { return (((pos >> 5) & 3) << 2) | (((pos >> 8) & 1) << 4); }
+  static NFLGPU_DEVFN int swz(int pos) { return (pos & (B - 1)) ^ swz_x(pos); }
+  // tile address of any position, whichever layout the configuration uses
+  static NFLGPU_DEVFN int taddr(int pos) { return SWZ ? swz(pos) : pad(pos); }
 };
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------
@@ -270,10 +284,27 @@ template <class C, int PASS> NFLGPU_DEVFN const typename C::TW *pass_tw(const ty
 }
 
 // tile <-> registers for pass PASS.  The last pass (c == 0) owns a whole padded row: 16-byte vector accesses.
-template <class C, int PASS> __device__ __forceinline__ void tile_load(typename C::Word (&x)[C::E], const typename C::Word *tile, int tid) {
+template <class C, int PASS> NFLGPU_DEVFN void tile_load(typename C::Word (&x)[C::E], const typename C::Word *tile, int tid) {
   typedef typename C::Word Word;
   constexpr int c = plan_c(C::n, C::WB, PASS);
-  if (c == 0) {
+  if (C::SWZ) {
+    // swz is linear over XOR: swz(T | K) = swz(T) ^ (K ^ swz_x(K)) for the thread part T and the register part K = k << c.
+    // The bits of K outside [4:2] are disjoint from everything else (they add), the rest selects one of a few XOR variants of the
+    // thread's base address: 2 in pass 0, 8 in pass 1, 4 (one per 16-byte vector) in pass 2.
+    const int base = C::swz(pass_pos<C, PASS>(tid, 0));
+    if (c == 0) {
+#pragma unroll
+      for (int v = 0; v < C::E / C::VEC; ++v) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(tile + (base ^ (v * C::VEC)));
+        const Word *w = reinterpret_cast<const Word *>(&t);
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) x[v * C::VEC + j] = w[j];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < C::E; ++k) x[k] = tile[(base ^ (((k << c) & 0x1c) ^ C::swz_x(k << c))) + ((k << c) & ~0x1c)];
+    }
+  } else if (c == 0) {
     const uint4 *row = reinterpret_cast<const uint4 *>(tile + (tid & (C::TPU - 1)) * C::ROW);
 #pragma unroll
     for (int v = 0; v < C::E / C::VEC; ++v) {
@@ -290,10 +321,25 @@ template <class C, int PASS> __device__ __forceinline__ void tile_load(typename 
     for (int k = 0; k < C::E; ++k) x[k] = base[C::pad_k(k << c)];
   }
 }
-template <class C, int PASS> __device__ __forceinline__ void tile_store(const typename C::Word (&x)[C::E], typename C::Word *tile, int tid) {
+template <class C, int PASS> NFLGPU_DEVFN void tile_store(const typename C::Word (&x)[C::E], typename C::Word *tile, int tid) {
   typedef typename C::Word Word;
   constexpr int c = plan_c(C::n, C::WB, PASS);
-  if (c == 0) {
+  if (C::SWZ) {  // (addresses as in tile_load)
+    const int base = C::swz(pass_pos<C, PASS>(tid, 0));
+    if (c == 0) {
+#pragma unroll
+      for (int v = 0; v < C::E / C::VEC; ++v) {
+        uint4 t;
+        Word *w = reinterpret_cast<Word *>(&t);
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) w[j] = x[v * C::VEC + j];
+        *reinterpret_cast<uint4 *>(tile + (base ^ (v * C::VEC))) = t;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < C::E; ++k) tile[(base ^ (((k << c) & 0x1c) ^ C::swz_x(k << c))) + ((k << c) & ~0x1c)] = x[k];
+    }
+  } else if (c == 0) {
     uint4 *row = reinterpret_cast<uint4 *>(tile + (tid & (C::TPU - 1)) * C::ROW);
 #pragma unroll
     for (int v = 0; v < C::E / C::VEC; ++v) {
@@ -320,7 +366,7 @@ template <class C> __device__ __forceinline__ void tile_to_gmem(const typename C
     const int ch = tid + j * C::TPU;
     if (CHUNKS % C::TPU != 0 && ch >= CHUNKS) break;
     const int pos = ch * C::VEC;
-    const uint4 t = *reinterpret_cast<const uint4 *>(tile + C::pad(pos));
+    const uint4 t = *reinterpret_cast<const uint4 *>(tile + C::taddr(pos));
     if (sizeof(Store) == sizeof(Word)) {
       *reinterpret_cast<uint4 *>(g + pos) = t;
     } else {  // 16-bit limbs: narrow 4 words to 4 limbs (8 bytes)
@@ -344,7 +390,7 @@ template <class C, int LB> __device__ __forceinline__ void tile_to_gmem_mul(cons
     const int ch = tid + j * C::TPU;
     if (CHUNKS % C::TPU != 0 && ch >= CHUNKS) break;
     const int pos = ch * C::VEC;
-    uint4 t = *reinterpret_cast<const uint4 *>(tile + C::pad(pos));
+    uint4 t = *reinterpret_cast<const uint4 *>(tile + C::taddr(pos));
     Word *w = reinterpret_cast<Word *>(&t);
     if (sizeof(Store) == sizeof(Word)) {
       const uint4 o = __ldg(reinterpret_cast<const uint4 *>(other + pos));
@@ -380,7 +426,7 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
       const uint2 i = ld_coef(reinterpret_cast<const uint2 *>(g + pos));
       t.x = i.x & 0xffffu; t.y = i.x >> 16; t.z = i.y & 0xffffu; t.w = i.y >> 16;
     }
-    *reinterpret_cast<uint4 *>(tile + C::pad(pos)) = t;
+    *reinterpret_cast<uint4 *>(tile + C::taddr(pos)) = t;
   }
 }
 

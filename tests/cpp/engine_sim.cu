@@ -55,6 +55,86 @@ template <class C> struct SimInv<C, -1> {
   static void run(typename C::Word *, const typename C::TW *, typename C::Word) {}
 };
 
+// The same transforms with the exchange between passes going through the kernels' own tile layout (tile_store / tile_load /
+// C::taddr: padded rows or the XOR swizzle), "thread" by "thread", the way ntt_fwd_kernel / ntt_inv_kernel use the tile:
+// forward = global -> registers -> pass S -> tile ... last pass -> tile -> 16-byte copy-out; inverse = 16-byte copy-in -> tile ->
+// passes NP-1 .. S+1 in the tile -> pass S from the tile -> global.  Single-tile shapes with more than one pass only.
+template <class C, int PASS> struct SimFwdTile {
+  static void run(typename C::Word *tile, const typename C::TW *tw, typename C::Word p) {
+    typedef typename C::Word Word;
+    const Word np = opaque_neg(p), twop = 2 * p;
+    for (int tid = 0; tid < C::TPU; ++tid) {
+      Word x[C::E];
+      tile_load<C, PASS>(x, tile, tid);
+      fwd_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), np, twop);
+      if (PASS == C::NP - 1)
+        for (int k = 0; k < C::E; ++k) x[k] = fwd_canon<C>(x[k], p, twop);
+      tile_store<C, PASS>(x, tile, tid);
+    }
+    SimFwdTile<C, PASS + 1>::run(tile, tw, p);
+  }
+};
+template <class C> struct SimFwdTile<C, C::NP> {
+  static void run(typename C::Word *, const typename C::TW *, typename C::Word) {}
+};
+template <class C, int PASS> struct SimInvTile {
+  static void run(typename C::Word *tile, const typename C::TW *tw, typename C::Word p) {
+    typedef typename C::Word Word;
+    const Word np = opaque_neg(p), twop = 2 * p;
+    const typename C::TW ninv = tw[C::N - 1];
+    for (int tid = 0; tid < C::TPU; ++tid) {
+      Word x[C::E];
+      tile_load<C, PASS>(x, tile, tid);
+      inv_pass<C, PASS>(x, pass_tw<C, PASS>(tw, tid), p, np, twop, ninv);
+      tile_store<C, PASS>(x, tile, tid);
+    }
+    SimInvTile<C, PASS - 1>::run(tile, tw, p);
+  }
+};
+template <class C> struct SimInvTile<C, 0> {
+  static void run(typename C::Word *, const typename C::TW *, typename C::Word) {}
+};
+
+template <int LB, int LOGN> int sim_tile(int inverse, uint64_t p, uint64_t root, uint64_t kmax, uint64_t *data) {
+  typedef NttCfg<LB, LOGN> C;
+  typedef typename C::Word Word;
+  typedef typename C::TW TW;
+  if (C::SPLIT != 0 || C::NP < 2) return -1;
+  ResidueTables t;
+  build_residue_tables(LB, C::WB, C::N, p, root, kmax, &t, false);
+  std::vector<TW> tw(C::N);
+  for (int i = 0; i < C::N; ++i) {
+    tw[i].x = (Word)(inverse ? t.inv_w[i] : t.fwd_w[i]);
+    tw[i].y = (Word)(inverse ? t.inv_ws[i] : t.fwd_ws[i]);
+  }
+  std::vector<Word> tile_store_buf(C::TILE_WORDS + 4, (Word)0xdeadbeef);
+  Word *tile = reinterpret_cast<Word *>(((uintptr_t)tile_store_buf.data() + 15) & ~(uintptr_t)15);  // 16-byte vectors
+  const Word np = opaque_neg((Word)p), twop = 2 * (Word)p;
+  if (!inverse) {
+    for (int tid = 0; tid < C::TPU; ++tid) {
+      Word x[C::E];
+      for (int k = 0; k < C::E; ++k) x[k] = (Word)data[pass_pos<C, 0>(tid, k)];
+      fwd_pass<C, 0>(x, pass_tw<C, 0>(tw.data(), tid), np, twop);
+      tile_store<C, 0>(x, tile, tid);
+    }
+    SimFwdTile<C, 1>::run(tile, tw.data(), (Word)p);
+    for (int ch = 0; ch < C::B / C::VEC; ++ch)  // tile_to_gmem
+      for (int j = 0; j < C::VEC; ++j) data[ch * C::VEC + j] = (uint64_t)tile[C::taddr(ch * C::VEC) + j];
+  } else {
+    for (int ch = 0; ch < C::B / C::VEC; ++ch)  // gmem_to_tile
+      for (int j = 0; j < C::VEC; ++j) tile[C::taddr(ch * C::VEC) + j] = (Word)data[ch * C::VEC + j];
+    SimInvTile<C, C::NP - 1>::run(tile, tw.data(), (Word)p);
+    const TW ninv = tw[C::N - 1];
+    for (int tid = 0; tid < C::TPU; ++tid) {
+      Word x[C::E];
+      tile_load<C, 0>(x, tile, tid);
+      inv_pass<C, 0>(x, pass_tw<C, 0>(tw.data(), tid), (Word)p, np, twop, ninv);
+      for (int k = 0; k < C::E; ++k) data[pass_pos<C, 0>(tid, k)] = (uint64_t)x[k];
+    }
+  }
+  return 0;
+}
+
 template <int LB, int LOGN> int sim_one(int inverse, uint64_t p, uint64_t root, uint64_t kmax, uint64_t *data) {
   typedef NttCfg<LB, LOGN> C;
   typedef typename C::Word Word;
@@ -116,6 +196,29 @@ extern "C" int nflsim_ntt(int limb_bits, int log2_degree, int inverse, uint64_t 
   } else if (limb_bits == 16) {
     switch (log2_degree) {
       SIM_CASE(16, 4) SIM_CASE(16, 5) SIM_CASE(16, 6) SIM_CASE(16, 7) SIM_CASE(16, 8) SIM_CASE(16, 9)
+    }
+  }
+  return -1;
+}
+
+#undef SIM_CASE
+#define SIM_CASE(LB, LOGN) \
+  case LOGN: return sim_tile<LB, LOGN>(inverse, p, root, kmax, data);
+// As nflsim_ntt, with the passes exchanging through the kernels' shared-memory tile layout (returns -1 for one-pass and split shapes).
+extern "C" int nflsim_ntt_tile(int limb_bits, int log2_degree, int inverse, uint64_t p, uint64_t root, uint64_t kmax, uint64_t *data) {
+  if (limb_bits == 64) {
+    switch (log2_degree) {
+      SIM_CASE(64, 6) SIM_CASE(64, 7) SIM_CASE(64, 8) SIM_CASE(64, 9) SIM_CASE(64, 10) SIM_CASE(64, 11) SIM_CASE(64, 12)
+      SIM_CASE(64, 13) SIM_CASE(64, 14)
+    }
+  } else if (limb_bits == 32) {
+    switch (log2_degree) {
+      SIM_CASE(32, 7) SIM_CASE(32, 8) SIM_CASE(32, 9) SIM_CASE(32, 10) SIM_CASE(32, 11) SIM_CASE(32, 12) SIM_CASE(32, 13)
+      SIM_CASE(32, 14) SIM_CASE(32, 15)
+    }
+  } else if (limb_bits == 16) {
+    switch (log2_degree) {
+      SIM_CASE(16, 7) SIM_CASE(16, 8) SIM_CASE(16, 9)
     }
   }
   return -1;

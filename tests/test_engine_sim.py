@@ -23,6 +23,7 @@ def sim():
         _lib = ctypes.CDLL(SIM_SO)
         _lib.nflsim_ntt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
                                     ctypes.c_void_p]
+        _lib.nflsim_ntt_tile.argtypes = _lib.nflsim_ntt.argtypes
         _lib.nflsim_pointwise.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64] + [ctypes.c_void_p] * 5 + [ctypes.c_size_t]
     return _lib
 
@@ -44,14 +45,15 @@ def run_pw(bits, M, op, a, b=None, c=None, d=None):
     return out
 
 
-def run_sim(bits, N, M, polys, inverse):
+def run_sim(bits, N, M, polys, inverse, tile=False):
     g = golden_params(bits)
     out = np.empty_like(polys)
     n = N.bit_length() - 1
+    fn = sim().nflsim_ntt_tile if tile else sim().nflsim_ntt
     for b in range(polys.shape[0]):
         for cm in range(M):
             d = np.ascontiguousarray(polys[b, cm].astype(np.uint64))
-            rc = sim().nflsim_ntt(bits, n, int(inverse), g["P"][cm], g["roots"][cm], g["kmax"], d.ctypes.data)
+            rc = fn(bits, n, int(inverse), g["P"][cm], g["roots"][cm], g["kmax"], d.ctypes.data)
             assert rc == 0, (bits, N)
             out[b, cm] = d.astype(DTYPES[bits])
     return out
@@ -85,6 +87,36 @@ def test_kernel_butterfly_networks_on_the_host_match_the_oracle(bits, N):
     assert np.array_equal(back, a)
     # the inverse on arbitrary canonical input (not only on forward outputs)
     assert np.array_equal(run_sim(bits, N, M, a, inverse=True), o.run("inv", a))
+
+
+TILE_SIZES = ([(64, 1 << n) for n in range(6, 15)] + [(32, 1 << n) for n in range(7, 16)] + [(16, 1 << n) for n in range(7, 10)])
+
+
+@pytest.mark.parametrize("bits,N", TILE_SIZES)
+def test_tile_exchange_layout_on_the_host(bits, N):
+    """The same networks with the passes exchanging through the kernels' own shared-memory tile addressing (tile_store / tile_load /
+    taddr: padded rows, or the XOR swizzle of the 32-bit N = 4096 shape) and the 16-byte copy-in / copy-out order."""
+    M = 2
+    o = Oracle(bits, N, M)
+    a = np.concatenate([random_polys(bits, N, M, 2 if N <= 4096 else 1, 7100 + N), edge_polys(bits, N, M)[3:5]])
+    want = o.run("fwd", a)
+    assert np.array_equal(run_sim(bits, N, M, a, inverse=False, tile=True), want)
+    assert np.array_equal(run_sim(bits, N, M, want, inverse=True, tile=True), a)
+
+
+def test_bank_conflict_model_of_every_tile_shape():
+    """tools/bank_conflicts.py: every pass and the 16-byte copies of every multi-pass shape reach the minimum number of shared-memory
+    wavefronts (the 32-bit N = 4096 shape only with its XOR swizzle); N <= 256 copies touch fewer than 32 lanes' worth and are exempt."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bank_conflicts", os.path.join(ROOT, "tools", "bank_conflicts.py"))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    for wb, n in [(64, k) for k in range(9, 15)] + [(32, k) for k in range(9, 16)]:
+        _, _, res = bc.analyse(wb, n, swz=(wb == 32 and n == 12))
+        for name, total, minimum in res:
+            assert total == minimum, (wb, n, name, total, minimum)
+    _, _, res = bc.analyse(32, 12, swz=False)
+    assert any(total > minimum for _, total, minimum in res)  # what the swizzle is for
 
 
 @pytest.mark.parametrize("bits,N", [(64, 256), (32, 256), (16, 128)])

@@ -165,6 +165,40 @@ def test_host_op_matches_device_path():
     assert np.array_equal(c.host_op("polymul", a[:64], b[:64]), o.run("polymul", a[:64], b[:64]))
 
 
+def test_host_op_async_ring_matches_blocking_calls():
+    """nflgpu_host_op_async + nflgpu_host_sync: several independent batches in flight through the chunk ring (more chunks than ring
+    slots, ragged tails, pageable and page-locked arrays, in place), bit-identical to the blocking call and to the oracle."""
+    bits, N, M, batch = 64, 1024, 4, 2600  # 81 MiB per operand: several chunks whatever NFLGPU_HOST_CHUNK_MIB is, ragged tail
+    c, o = ctx_for(bits, N, M), Oracle(bits, N, M)
+    a = random_polys(bits, N, M, batch, 15)
+    b = random_polys(bits, N, M, batch, 16)
+    fa = c.host_op("fwd", a)
+    assert np.array_equal(fa[-3:], o.run("fwd", a[-3:]))
+    o1, o2, o3 = np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)
+    c.host_op("fwd", a, out=o1, wait=False)
+    c.host_op("inv", fa, out=o2, wait=False)
+    c.host_op("mul", a, b, out=o3, wait=False)
+    c.host_sync()
+    assert np.array_equal(o1, fa) and np.array_equal(o2, a)
+    assert np.array_equal(o3[::97], o.run("mul", a[::97], b[::97])) and np.array_equal(o3, c.host_op("mul", a, b))
+    # in place on a pageable array, then the same on page-locked memory, with a one-poly call queued behind the big one
+    x, one = a.copy(), a[:1].copy()
+    c.host_op("fwd", x, out=x, wait=False)
+    c.host_op("fwd", one, out=one, wait=False)
+    c.host_sync()
+    assert np.array_equal(x, fa) and np.array_equal(one, fa[:1])
+    y = fa.copy()
+    c.host_register(y)
+    try:
+        c.host_op("inv", y, out=y, wait=False)
+        c.host_sync()
+        assert np.array_equal(y, a)
+    finally:
+        c.host_unregister(y)
+    c.host_sync()  # nothing in flight: returns at once
+    assert np.array_equal(c.host_op("fwd", a[:5]), fa[:5])  # a blocking call after asynchronous ones
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libnflref.so did not travel")
 def test_live_reference_side_by_side():
     # (64, 32768, 2) is the largest configuration of the reference's own test matrix (tests/CMakeLists.txt:1-7)
