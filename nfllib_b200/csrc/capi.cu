@@ -1147,13 +1147,11 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
     }
   }
 
-  // Chunk size and ring depth, measured on B200 / PCIe gen5 (profiles/r02_variants.log, block "host pipeline"): copies of 8 MiB
-  // and more run at the rate of whole-array copies (48 GB/s each way at once), smaller ones lose 8-35 %; the ring only has to
-  // cover upload + kernel + download of one chunk.  The first and last chunks of a call are shorter (C/8, C/8, C/4, C/2, C ... C,
-  // C/2, C/4, C/8, C/8): nothing overlaps the first upload and the last download, so they should be small.
+  // Chunk size and ring depth, measured on B200 / PCIe gen5 (profiles/r02_variants.log, block 7): copies of 8 MiB and more run at
+  // the rate of whole-array copies (48 GB/s each way at once), smaller ones lose 8-35 %, so short first and last chunks (a ramp
+  // C/8, C/8, C/4, C/2, C ... was built and measured) do not pay; the ring only has to cover upload + kernel + download of one chunk.
   static const size_t chunk_bytes = (size_t)env_long("NFLGPU_HOST_CHUNK_MIB", 1, 1024, 16) << 20;
   static const int ring_want = (int)env_long("NFLGPU_HOST_RING", 2, HostPipe::kMaxRing, 4);
-  static const bool ramp = env_long("NFLGPU_HOST_RAMP", 0, 1, 1) == 1;
   size_t chunk = chunk_bytes / poly_bytes;
   if (chunk == 0) chunk = 1;
   if (chunk > batch) chunk = batch;
@@ -1190,22 +1188,11 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
   // a call that fits one chunk has nothing to overlap: all three steps go on one stream (no event hops on the latency path)
   const bool single = batch <= chunk;
   cudaStream_t sin = single ? p.run : p.in, sout = single ? p.run : p.out;
-  // ramp: chunk sizes C/8, C/8, C/4, C/2 at both ends of a call that is long enough to have a middle
-  size_t steps[4] = {chunk / 8, chunk / 8, chunk / 4, chunk / 2}, ramp_total = 0;
-  for (size_t &v : steps) { if (v == 0) v = 1; ramp_total += v; }
-  const bool ramped = ramp && batch >= 2 * ramp_total + chunk;
-  int head = 0, tail = 0;
   for (size_t done = 0; done < batch;) {
     HostSlot &s = p.slot[p.next];
     int rc = host_retire(s);  // the chunk that used this slot `ring` chunks ago
     if (rc != NFLGPU_OK) { host_abort(ctx); return rc; }
-    size_t cnt = (batch - done < chunk) ? batch - done : chunk;
-    if (ramped) {
-      const size_t left = batch - done;
-      if (head < 4) cnt = steps[head++];
-      else if (left > ramp_total) cnt = left - ramp_total < chunk ? left - ramp_total : chunk;  // the middle ends where the tail begins
-      else cnt = steps[3 - tail++];
-    }
+    const size_t cnt = (batch - done < chunk) ? batch - done : chunk;
     const size_t bytes = cnt * poly_bytes;
     for (int i = 0; i < nin; ++i) {
       const char *src = static_cast<const char *>(in[i]) + done * poly_bytes;
