@@ -1006,29 +1006,7 @@ int nflgpu_gather_residues(nflgpu_ctx *ctx, void *dst_full, const void *const *s
 
 // ---- host-buffer pipeline ------------------------------------------------------------------------------------
 
-// Staging copies between pageable user memory and the pinned buffers: one host thread moves ~8-10 GB/s, which would cap the
-// pageable path far below PCIe; a few threads on disjoint slices bring it to the DMA rate (NFLGPU_HOST_COPY_THREADS, default min(8, half the host's hardware threads)).
-static void staging_copy(void *dst, const void *src, size_t bytes) {
-  static const unsigned want = [] {
-    const char *e = std::getenv("NFLGPU_HOST_COPY_THREADS");
-    long hw = (long)std::thread::hardware_concurrency() / 2;
-    long v = e ? std::atol(e) : (hw < 2 ? 2 : hw > 8 ? 8 : hw);
-    return (unsigned)(v < 1 ? 1 : v > 16 ? 16 : v);
-  }();
-  const unsigned nt = bytes >= ((size_t)2 << 20) ? want : 1;
-  if (nt == 1) { std::memcpy(dst, src, bytes); return; }
-  const size_t slice = ((bytes / nt) + 4095) & ~(size_t)4095;
-  std::thread th[16];
-  unsigned started = 0;
-  for (unsigned t = 1; t < nt; ++t) {
-    const size_t off = (size_t)t * slice;
-    if (off >= bytes) break;
-    const size_t len = bytes - off < slice ? bytes - off : slice;
-    th[started++] = std::thread([=] { std::memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
-  }
-  std::memcpy(dst, src, slice < bytes ? slice : bytes);
-  for (unsigned t = 0; t < started; ++t) th[t].join();
-}
+// (staging copies between pageable user memory and the pinned ring buffers: host_copy.cpp)
 
 int nflgpu_host_register(nflgpu_ctx *ctx, void *host_ptr, size_t bytes) {
   if (!ctx || !host_ptr || bytes == 0) { set_error("null argument"); return NFLGPU_ERR_ARG; }
@@ -1150,9 +1128,13 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
   // Chunk size and ring depth, measured on B200 / PCIe gen5 (profiles/r02_variants.log, block 7): copies of 8 MiB and more run at
   // the rate of whole-array copies (48 GB/s each way at once), smaller ones lose 8-35 %, so short first and last chunks (a ramp
   // C/8, C/8, C/4, C/2, C ... was built and measured) do not pay; the ring only has to cover upload + kernel + download of one chunk.
+  // Blocking calls use 16 MiB chunks (their first upload and last download overlap nothing, so they should be short); asynchronous
+  // calls stream, pay no fill or drain, and use 32 MiB chunks: the copy engines slow down while a transform kernel runs, and fewer,
+  // fuller launches spend less time in kernels (streamed step: 5.92 ms with 16 MiB chunks, 5.72 ms with 32 MiB, 5.53 ms without kernels).
   static const size_t chunk_bytes = (size_t)env_long("NFLGPU_HOST_CHUNK_MIB", 1, 1024, 16) << 20;
+  static const size_t chunk_bytes_async = (size_t)env_long("NFLGPU_HOST_ASYNC_CHUNK_MIB", 1, 1024, env_long("NFLGPU_HOST_CHUNK_MIB", 1, 1024, 32)) << 20;
   static const int ring_want = (int)env_long("NFLGPU_HOST_RING", 2, HostPipe::kMaxRing, 4);
-  size_t chunk = chunk_bytes / poly_bytes;
+  size_t chunk = (wait ? chunk_bytes : chunk_bytes_async) / poly_bytes;
   if (chunk == 0) chunk = 1;
   if (chunk > batch) chunk = batch;
   if (p.slot_bytes < chunk * poly_bytes || p.ring == 0) {  // (re)build the ring; buffers only ever grow

@@ -34,5 +34,8 @@ void build_residue_tables(int limb_bits, int word_bits, size_t N, uint64_t p, ui
 
 void set_error(const std::string &msg);
 
+// pageable <-> pinned staging copy of the host-buffer pipeline (host_copy.cpp: copy-thread pool, non-temporal stores)
+void staging_copy(void *dst, const void *src, size_t bytes);
+
 }  // namespace nflgpu
 #endif
