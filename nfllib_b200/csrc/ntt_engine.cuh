@@ -122,6 +122,20 @@ template <int LB, int LOGN> struct NttCfg {
 #else
   static constexpr bool HOP = DYNAMIC && !TW_SMEM;
 #endif
+  // Software pipelining across units: the inverse kernel copies the NEXT unit's slab into the tile with cp.async (no registers) while
+  // the current unit's final pass computes and stores -- the tile is free from the moment every thread has loaded its last-pass
+  // window -- and the forward kernel issues the next unit's pass-0 loads before the current unit's copy-out instead of after it.
+  // Measured on B200 (profiles/r02_variants.log block 8, -DNFLGPU_PIPE=1 against the tree): inverse N = 4096 u64 -3.5 %, C4 (u32
+  // N = 4096) -2.1 %, C5 -0.6 %, C3 -0.9 %, but N = 1024 u64 +1.5 % (its 14 units per SM already overlap); forward C4 -1.8 %, every
+  // 64-bit size +1.1 .. +1.6 % (64 more live registers through the copy-out).  So: inverse from N = 4096 up, forward for C4's shape only.
+  // -DNFLGPU_PIPE=0/1 forces it off / on everywhere.
+#ifdef NFLGPU_PIPE
+  static constexpr bool PIPE_INV = NFLGPU_PIPE != 0 && (NP - SPLIT) > 1 && sizeof(Store) == sizeof(Word);
+  static constexpr bool PIPE_FWD = NFLGPU_PIPE != 0 && (NP - SPLIT) > 1;
+#else
+  static constexpr bool PIPE_INV = n >= 12 && (NP - SPLIT) > 1 && sizeof(Store) == sizeof(Word);
+  static constexpr bool PIPE_FWD = WB == 32 && n == 12 && (NP - SPLIT) > 1;
+#endif
   static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
   static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
@@ -430,6 +444,20 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
   }
 }
 
+// the same copy issued as cp.async (LDGSTS: global -> shared without passing through registers); completion: cp_async_wait()
+template <class C> __device__ __forceinline__ void gmem_to_tile_async(typename C::Word *tile, const typename C::Store *g, int tid) {
+  static_assert(sizeof(typename C::Store) == sizeof(typename C::Word), "cp.async copies limbs as they are");
+  constexpr int CHUNKS = C::B / C::VEC;
+#pragma unroll
+  for (int j = 0; j < (CHUNKS + C::TPU - 1) / C::TPU; ++j) {
+    const int ch = tid + j * C::TPU;
+    if (CHUNKS % C::TPU != 0 && ch >= CHUNKS) break;
+    const int pos = ch * C::VEC;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(tile + C::taddr(pos))), "l"(g + pos) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- pass chains (compile-time recursion over the passes) ---------------------------------------------------
 
 // forward: passes SPLIT+1 .. NP-1 after pass SPLIT has stored its result into the tile (the caller has synchronised the slot)
@@ -602,6 +630,15 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const TW *tw = stage_twiddles<C>(a, cm, smem);
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base, hop > 0);
+  Word x[C::E];
+  // pass-0 window of sub-block j, straight from global memory: for fixed k the threads touch consecutive limbs
+  auto load_window = [&](uint32_t j) {
+    const size_t ub = ((size_t)(j >> C::LOGG) * a.nmoduli + cm) * C::N;
+    const int t = (int)((j & ((1u << C::LOGG) - 1)) * C::TPU) + tl;
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ub + pass_pos<C, S>(t, k));
+  };
+  if (C::PIPE_FWD && walk.index() < nblocks) load_window(walk.index());
   for (; walk.index() < nblocks; walk.advance()) {
     walk.claim_ahead();
     const uint32_t j = walk.index();
@@ -609,15 +646,15 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
     const int tid = (int)(g * C::TPU) + tl;  // index inside the whole unit
     if (!C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // static walk: the next index is known now
-    Word x[C::E];
-    // the first tile pass reads straight from global memory: for fixed k the threads touch consecutive limbs
+    if (!C::PIPE_FWD) {
 #if defined(NFLGPU_ABL) && (NFLGPU_ABL & 1)  // timing experiment: no global loads (results are wrong)
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = (Word)(ubase + pass_pos<C, S>(tid, k)) * 0x9E3779B97F4A7C15ull >> 3;
+      for (int k = 0; k < C::E; ++k) x[k] = (Word)(ubase + pass_pos<C, S>(tid, k)) * 0x9E3779B97F4A7C15ull >> 3;
 #else
 #pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, S>(tid, k));
+      for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, S>(tid, k));
 #endif
+    }
     fwd_pass<C, S>(x, pass_tw<C, S>(tw, tid), np, twop);
     if (C::NP - S == 1) {
 #pragma unroll
@@ -632,9 +669,11 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
       tile_store<C, S>(x, tile, tid);
       walk.publish();
       unit_sync<C>(slot, lane_base);
+      const uint32_t jn = C::PIPE_FWD ? walk.peek_next() : 0xffffffffu;
       if (C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // the leader's claim has just been published
       FwdChain<C, S + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
       unit_sync<C>(slot, lane_base);
+      if (C::PIPE_FWD && jn < nblocks) load_window(jn);  // (PIPE_FWD) in flight while the tile is copied out
 #if defined(NFLGPU_ABL) && (NFLGPU_ABL & 2)  // timing experiment: one store per unit instead of the copy-out
       if (tl == 0) dst[bbase] = (Store)tile[0];
 #else
@@ -671,17 +710,31 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const TW ninv = tw[C::N - 1];
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
+  auto slab_of = [&](uint32_t j) { return src + ((size_t)(j >> C::LOGG) * a.nmoduli + cm) * C::N + (size_t)(j & ((1u << C::LOGG) - 1)) * C::B; };
+  if constexpr (C::PIPE_INV) {
+    if (walk.index() < nblocks) gmem_to_tile_async<C>(tile, slab_of(walk.index()), tl);
+  }
   for (; walk.index() < nblocks; walk.advance()) {
     walk.claim_ahead();
     const uint32_t j = walk.index();
     const uint32_t b = j >> C::LOGG, g = j & ((1u << C::LOGG) - 1);
     const size_t ubase = ((size_t)b * a.nmoduli + cm) * C::N;
     const int tid = (int)(g * C::TPU) + tl;
-    if (!C::DYNAMIC) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);
+    if (!C::DYNAMIC && !C::PIPE_INV) next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);
     Word x[C::E];
     if (C::NP - S == 1) {
 #pragma unroll
       for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, S>(tid, k));
+    } else if constexpr (C::PIPE_INV) {
+      cp_async_wait();  // this thread's part of the sub-block (issued during the previous iteration) has landed
+      walk.publish();
+      unit_sync<C>(slot, lane_base);  // ... and everybody else's; the leader's claim is visible
+      const uint32_t jn = walk.peek_next();
+      InvChain<C, C::NP - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);
+      unit_sync<C>(slot, lane_base);
+      tile_load<C, S>(x, tile, tid);
+      unit_sync<C>(slot, lane_base);  // every thread holds its last-pass window: the tile is free for the next sub-block
+      if (jn < nblocks) gmem_to_tile_async<C>(tile, slab_of(jn), tl);  // lands while the last pass computes and stores
     } else {
       if (!C::DYNAMIC) unit_sync<C>(slot, lane_base);  // previous sub-block's last pass has finished reading the tile (advance() syncs in dynamic mode)
       gmem_to_tile<C>(tile, src + ubase + (size_t)g * C::B, tl);

@@ -57,9 +57,44 @@ static int run(int bits, size_t N, size_t M, size_t batch, int launches) {
   return bad;
 }
 
+// The host-buffer ring (nflgpu_host_op_async / nflgpu_host_sync: three streams, events, pinned staging) on pageable arrays: two
+// independent batches in flight, forward then inverse, more chunks than ring slots.
+static int run_host(int bits, size_t N, size_t M, size_t batch) {
+  nflgpu_ctx *ctx = nullptr;
+  CHECK(nflgpu_ctx_create(&ctx, bits, N, M, 0, 0, nullptr, nullptr));
+  std::vector<uint64_t> P(M);
+  CHECK(nflgpu_ctx_moduli(ctx, P.data()));
+  const size_t limb = bits / 8, bytes = nflgpu_batch_bytes(ctx, batch);
+  std::vector<unsigned char> a(bytes), c(bytes), fa(bytes), fc(bytes), ra(bytes), rc(bytes);
+  uint64_t s = 0x9E3779B97F4A7C15ull + N + batch;
+  for (std::vector<unsigned char> *h : {&a, &c})
+    for (size_t b = 0; b < batch; ++b)
+      for (size_t cm = 0; cm < M; ++cm)
+        for (size_t i = 0; i < N; ++i) {
+          s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+          const uint64_t v = s % P[cm];
+          std::memcpy(&(*h)[((b * M + cm) * N + i) * limb], &v, limb);
+        }
+  CHECK(nflgpu_host_op_async(ctx, 0, fa.data(), a.data(), nullptr, nullptr, batch));
+  CHECK(nflgpu_host_op_async(ctx, 0, fc.data(), c.data(), nullptr, nullptr, batch));
+  CHECK(nflgpu_host_sync(ctx));
+  CHECK(nflgpu_host_op_async(ctx, 1, ra.data(), fa.data(), nullptr, nullptr, batch));
+  CHECK(nflgpu_host_op_async(ctx, 1, rc.data(), fc.data(), nullptr, nullptr, batch));
+  CHECK(nflgpu_host_op(ctx, 1, fc.data(), fc.data(), nullptr, nullptr, batch));  // blocking, in place, behind the asynchronous ones
+  const int bad = std::memcmp(ra.data(), a.data(), bytes) != 0 || std::memcmp(rc.data(), c.data(), bytes) != 0 || std::memcmp(fc.data(), c.data(), bytes) != 0;
+  std::printf("u%d N=%zu M=%zu batch=%zu: host ring, 2 x (fwd, inv) asynchronous + 1 blocking in place: %s\n", bits, N, M, batch, bad ? "MISMATCH" : "ok");
+  nflgpu_ctx_destroy(ctx);
+  return bad;
+}
+
 int main(int argc, char **argv) {
   const int launches = argc > 1 ? std::atoi(argv[1]) : 300;
   int bad = 0;
+  // more units than unit slots: the software-pipelined kernels (ntt_engine.cuh PIPE_INV / PIPE_FWD) prefetch their next unit
+  bad |= run(32, 4096, 2, 1500, launches / 8 + 1);
+  bad |= run(64, 4096, 2, 500, launches / 8 + 1);
+  bad |= run(64, 8192, 1, 700, launches / 8 + 1);
+  bad |= run_host(64, 1024, 4, 2600);
   bad |= run(64, 2048, 3, 37, launches);     // dynamic unit walk, two-pass tile
   bad |= run(64, 2048, 3, 1, launches);
   bad |= run(32, 4096, 2, 3, launches);
