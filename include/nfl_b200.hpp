@@ -820,6 +820,15 @@ template <class P> void ntt_pow_phi(P *polys, size_t count) {
 template <class P> void invntt_pow_invphi(P *polys, size_t count) {
   detail::check(nflgpu_host_op(P::backend_type::get().ctx, 1, polys, polys, nullptr, nullptr, count), "invntt_pow_invphi[]");
 }
+// The same without the final wait (nflgpu_host_op_async): several arrays can be in flight, the uploads of one running under the
+// downloads of the previous one; the arrays must stay alive and untouched until host_sync<P>() returns.
+template <class P> void ntt_pow_phi_async(P *polys, size_t count) {
+  detail::check(nflgpu_host_op_async(P::backend_type::get().ctx, 0, polys, polys, nullptr, nullptr, count), "ntt_pow_phi_async[]");
+}
+template <class P> void invntt_pow_invphi_async(P *polys, size_t count) {
+  detail::check(nflgpu_host_op_async(P::backend_type::get().ctx, 1, polys, polys, nullptr, nullptr, count), "invntt_pow_invphi_async[]");
+}
+template <class P> void host_sync() { detail::check(nflgpu_host_sync(P::backend_type::get().ctx), "nflgpu_host_sync"); }
 // Page-locks a host array of polys for the lifetime of the guard (nflgpu_host_register): the host-buffer calls above then
 // DMA it directly instead of staging it through pinned buffers.  Destroy the guard before freeing the array.
 template <class P> class pinned_region {

@@ -92,6 +92,22 @@ template <class P> static int run(const char *fa, const char *fb, size_t count, 
     REQUIRE(same(c, x));
     c.ntt_pow_phi(); REQUIRE(!same(c, x));
     c.invntt_pow_invphi(); REQUIRE(same(c, x));               // poly_p.cpp:52-58, strong form
+    // whole host arrays through the host-buffer ring: blocking and asynchronous forms against the per-poly calls
+    {
+      P *arr = alloc_polys<P>(6), *brr = alloc_polys<P>(6);
+      for (int i = 0; i < 6; ++i) { arr[i] = (i & 1) ? y : x; brr[i] = (i & 1) ? x : y; }
+      P fx = x, fy = y; fx.ntt_pow_phi(); fy.ntt_pow_phi();
+      nfl::cuda::ntt_pow_phi(arr, 6);
+      nfl::cuda::ntt_pow_phi_async(brr, 6);
+      nfl::cuda::host_sync<P>();
+      for (int i = 0; i < 6; ++i) { REQUIRE(same(arr[i], (i & 1) ? fy : fx)); REQUIRE(same(brr[i], (i & 1) ? fx : fy)); }
+      nfl::cuda::invntt_pow_invphi_async(arr, 6);
+      nfl::cuda::invntt_pow_invphi_async(brr, 6);
+      nfl::cuda::host_sync<P>();
+      for (int i = 0; i < 6; ++i) { REQUIRE(same(arr[i], (i & 1) ? y : x)); REQUIRE(same(brr[i], (i & 1) ? x : y)); }
+      for (int i = 0; i < 6; ++i) { arr[i].~P(); brr[i].~P(); }
+      std::free(arr); std::free(brr);
+    }
     // == is "any coefficient equal", != is "any coefficient differs" (ops.hpp:81-95)
     REQUIRE(bool(x == x)); REQUIRE(!bool(x != x)); REQUIRE(bool(x != (x + P(1))));
     e = x; e(0, 0) = static_cast<T>((e(0, 0) + 1) % P::get_modulus(0));
