@@ -136,6 +136,23 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr bool PIPE_INV = n >= 12 && (NP - SPLIT) > 1 && sizeof(Store) == sizeof(Word);
   static constexpr bool PIPE_FWD = WB == 32 && n == 12 && (NP - SPLIT) > 1;
 #endif
+  // Short first pass (r0 < e stages): the low e - r0 bits of the register index are independent columns.  With adjacent columns --
+  // position = (k_hi << (n - r0)) | (tid << CB) | k_lo -- pass 0 moves them as 16-byte vectors: LDG.128 from HBM / STS.128 into the
+  // tile in the forward kernel, LDS.128 / STG.128 in the inverse kernel, half the load / store instructions of the 8-byte
+  // column-strided form (pass_pos, window_load / window_store below).  Measured on B200 against the strided form (-DNFLGPU_ADJ=0,
+  // profiles/r02_variants.log block 9): N = 1024 (two column bits: 32 bytes per lane, two half-used sectors per request) +1.7 %
+  // forward / +3.7 % inverse, N = 2048 +0.7 / -0.3 %, N = 16384 (one column bit, 16 bytes per lane) -0.4 / -1.4 %.  So it is on for
+  // the N = 16384 shape only; -DNFLGPU_ADJ=1 turns it on wherever the tile layout stays conflict free (one column bit, or two with
+  // 16-coefficient rows: tools/bank_conflicts.py), -DNFLGPU_ADJ=0 off everywhere.
+  static constexpr int CB0 = (WB == 64 && SPLIT == 0 && NP > 1) ? e - plan_r(n, WB, 0) : 0;
+#if defined(NFLGPU_ADJ) && NFLGPU_ADJ == 0
+  static constexpr int CB = 0;
+#elif defined(NFLGPU_ADJ)
+  static constexpr int CB = (CB0 == 1 || (CB0 == 2 && e == 4)) ? CB0 : 0;
+#else
+  static constexpr int CB = (CB0 == 1 && n == 14) ? 1 : 0;
+#endif
+  static constexpr bool ADJ = CB >= 1;
   static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
   static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
@@ -155,8 +172,8 @@ template <int LB, int LOGN> struct NttCfg {
 // Coefficient loads.  The kernels support dst == src (nflgpu_polymul's inverse, batch::ntt_pow_phi): every word of a slab is read
 // exactly once, by the unit that later overwrites it, before any of that unit's stores -- the invariant that makes the
 // non-coherent path (ld.global.nc) legal there.  -DNFLGPU_PLAIN_LD switches to ordinary loads (measured: no difference).
-template <class T> __device__ __forceinline__ T ld_coef(const T *p) {
-#ifdef NFLGPU_PLAIN_LD
+template <class T> NFLGPU_DEVFN T ld_coef(const T *p) {
+#if defined(NFLGPU_PLAIN_LD) || !defined(__CUDA_ARCH__)
   return *p;
 #else
   return __ldg(p);
@@ -225,6 +242,10 @@ template <class C> __device__ __forceinline__ void unit_sync(int slot, int lane_
 // unit: for split transforms (sub-block number << log2(TPU)) | index inside the sub-block
 template <class C, int PASS> NFLGPU_DEVFN int pass_pos(int tid, int k) {
   constexpr int hi = plan_hi(C::n, C::WB, PASS), c = plan_c(C::n, C::WB, PASS);
+  if (PASS == 0 && C::ADJ) {  // adjacent columns: the butterfly bits of k on top, the thread in the middle, the column below
+    constexpr int r0 = plan_r(C::n, C::WB, 0);
+    return ((k >> C::CB) << (C::n - r0)) | (tid << C::CB) | (k & ((1 << C::CB) - 1));
+  }
   const int g = tid >> c, l = tid & ((1 << c) - 1);
   return (g << hi) | (k << c) | l;
 }
@@ -301,7 +322,20 @@ template <class C, int PASS> NFLGPU_DEVFN const typename C::TW *pass_tw(const ty
 template <class C, int PASS> NFLGPU_DEVFN void tile_load(typename C::Word (&x)[C::E], const typename C::Word *tile, int tid) {
   typedef typename C::Word Word;
   constexpr int c = plan_c(C::n, C::WB, PASS);
-  if (C::SWZ) {
+  if (PASS == 0 && C::ADJ) {  // adjacent columns: 2^CB consecutive words per butterfly index, 16-byte vectors (padded layout only)
+    constexpr int r0 = plan_r(C::n, C::WB, 0), COLS = 1 << C::CB;
+    const Word *base = tile + C::pad(tid << C::CB);
+#pragma unroll
+    for (int kh = 0; kh < (1 << r0); ++kh) {
+#pragma unroll
+      for (int v = 0; v < COLS / C::VEC; ++v) {
+        const uint4 t = *reinterpret_cast<const uint4 *>(base + C::pad_k(kh << (C::n - r0)) + v * C::VEC);
+        const Word *w = reinterpret_cast<const Word *>(&t);
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) x[kh * COLS + v * C::VEC + j] = w[j];
+      }
+    }
+  } else if (C::SWZ) {
     // swz is linear over XOR: swz(T | K) = swz(T) ^ (K ^ swz_x(K)) for the thread part T and the register part K = k << c.
     // The bits of K outside [4:2] are disjoint from everything else (they add), the rest selects one of a few XOR variants of the
     // thread's base address: 2 in pass 0, 8 in pass 1, 4 (one per 16-byte vector) in pass 2.
@@ -338,7 +372,21 @@ template <class C, int PASS> NFLGPU_DEVFN void tile_load(typename C::Word (&x)[C
 template <class C, int PASS> NFLGPU_DEVFN void tile_store(const typename C::Word (&x)[C::E], typename C::Word *tile, int tid) {
   typedef typename C::Word Word;
   constexpr int c = plan_c(C::n, C::WB, PASS);
-  if (C::SWZ) {  // (addresses as in tile_load)
+  if (PASS == 0 && C::ADJ) {  // (addresses as in tile_load)
+    constexpr int r0 = plan_r(C::n, C::WB, 0), COLS = 1 << C::CB;
+    Word *base = tile + C::pad(tid << C::CB);
+#pragma unroll
+    for (int kh = 0; kh < (1 << r0); ++kh) {
+#pragma unroll
+      for (int v = 0; v < COLS / C::VEC; ++v) {
+        uint4 t;
+        Word *w = reinterpret_cast<Word *>(&t);
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) w[j] = x[kh * COLS + v * C::VEC + j];
+        *reinterpret_cast<uint4 *>(base + C::pad_k(kh << (C::n - r0)) + v * C::VEC) = t;
+      }
+    }
+  } else if (C::SWZ) {  // (addresses as in tile_load)
     const int base = C::swz(pass_pos<C, PASS>(tid, 0));
     if (c == 0) {
 #pragma unroll
@@ -441,6 +489,51 @@ template <class C> __device__ __forceinline__ void gmem_to_tile(typename C::Word
       t.x = i.x & 0xffffu; t.y = i.x >> 16; t.z = i.y & 0xffffu; t.w = i.y >> 16;
     }
     *reinterpret_cast<uint4 *>(tile + C::taddr(pos)) = t;
+  }
+}
+
+// pass-0 register window <-> the unit's slab in global memory (SPLIT == 0: `tid` is the thread's index inside the unit).  For
+// fixed k the threads touch consecutive limbs (8 bytes per lane), or with adjacent columns consecutive 16-byte vectors.
+template <class C> NFLGPU_DEVFN void window_load(typename C::Word (&x)[C::E], const typename C::Store *unit, int tid) {
+  typedef typename C::Word Word;
+  if (C::ADJ) {
+    constexpr int r0 = plan_r(C::n, C::WB, 0), COLS = 1 << C::CB;
+    const typename C::Store *base = unit + (tid << C::CB);
+#pragma unroll
+    for (int kh = 0; kh < (1 << r0); ++kh) {
+#pragma unroll
+      for (int v = 0; v < COLS / C::VEC; ++v) {
+        const uint4 t = ld_coef(reinterpret_cast<const uint4 *>(base + (kh << (C::n - r0)) + v * C::VEC));
+        const Word *w = reinterpret_cast<const Word *>(&t);
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) x[kh * COLS + v * C::VEC + j] = w[j];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(unit + pass_pos<C, C::SPLIT>(tid, k));
+  }
+}
+template <class C> NFLGPU_DEVFN void window_store(const typename C::Word (&x)[C::E], typename C::Store *unit, int tid) {
+  typedef typename C::Word Word;
+  typedef typename C::Store Store;
+  if (C::ADJ) {
+    constexpr int r0 = plan_r(C::n, C::WB, 0), COLS = 1 << C::CB;
+    Store *base = unit + (tid << C::CB);
+#pragma unroll
+    for (int kh = 0; kh < (1 << r0); ++kh) {
+#pragma unroll
+      for (int v = 0; v < COLS / C::VEC; ++v) {
+        uint4 t;
+        Word *w = reinterpret_cast<Word *>(&t);
+#pragma unroll
+        for (int j = 0; j < C::VEC; ++j) w[j] = x[kh * COLS + v * C::VEC + j];
+        *reinterpret_cast<uint4 *>(base + (kh << (C::n - r0)) + v * C::VEC) = t;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < C::E; ++k) unit[pass_pos<C, C::SPLIT>(tid, k)] = (Store)x[k];
   }
 }
 
@@ -635,8 +728,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   auto load_window = [&](uint32_t j) {
     const size_t ub = ((size_t)(j >> C::LOGG) * a.nmoduli + cm) * C::N;
     const int t = (int)((j & ((1u << C::LOGG) - 1)) * C::TPU) + tl;
-#pragma unroll
-    for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ub + pass_pos<C, S>(t, k));
+    window_load<C>(x, src + ub, t);
   };
   if (C::PIPE_FWD && walk.index() < nblocks) load_window(walk.index());
   for (; walk.index() < nblocks; walk.advance()) {
@@ -651,8 +743,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #pragma unroll
       for (int k = 0; k < C::E; ++k) x[k] = (Word)(ubase + pass_pos<C, S>(tid, k)) * 0x9E3779B97F4A7C15ull >> 3;
 #else
-#pragma unroll
-      for (int k = 0; k < C::E; ++k) x[k] = (Word)ld_coef(src + ubase + pass_pos<C, S>(tid, k));
+      window_load<C>(x, src + ubase, tid);
 #endif
     }
     fwd_pass<C, S>(x, pass_tw<C, S>(tw, tid), np, twop);
@@ -747,8 +838,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
     }
     inv_pass<C, S>(x, pass_tw<C, S>(tw, tid), p, np, twop, ninv);
     // this pass writes straight to global memory (lane-contiguous for fixed k)
-#pragma unroll
-    for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, S>(tid, k)] = (Store)x[k];
+    window_store<C>(x, dst + ubase, tid);
   }
   UnitWalk<C>::finish(a);
 }

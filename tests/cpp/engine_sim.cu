@@ -110,10 +110,12 @@ template <int LB, int LOGN> int sim_tile(int inverse, uint64_t p, uint64_t root,
   std::vector<Word> tile_store_buf(C::TILE_WORDS + 4, (Word)0xdeadbeef);
   Word *tile = reinterpret_cast<Word *>(((uintptr_t)tile_store_buf.data() + 15) & ~(uintptr_t)15);  // 16-byte vectors
   const Word np = opaque_neg((Word)p), twop = 2 * (Word)p;
+  std::vector<typename C::Store> slab(C::N + 2);  // the unit as it lies in global memory (limbs, 16-byte aligned like a batch buffer)
+  for (int i = 0; i < C::N; ++i) slab[i] = (typename C::Store)data[i];
   if (!inverse) {
     for (int tid = 0; tid < C::TPU; ++tid) {
       Word x[C::E];
-      for (int k = 0; k < C::E; ++k) x[k] = (Word)data[pass_pos<C, 0>(tid, k)];
+      window_load<C>(x, slab.data(), tid);  // the kernels' own pass-0 global-memory access (8-byte columns or 16-byte vectors)
       fwd_pass<C, 0>(x, pass_tw<C, 0>(tw.data(), tid), np, twop);
       tile_store<C, 0>(x, tile, tid);
     }
@@ -129,8 +131,9 @@ template <int LB, int LOGN> int sim_tile(int inverse, uint64_t p, uint64_t root,
       Word x[C::E];
       tile_load<C, 0>(x, tile, tid);
       inv_pass<C, 0>(x, pass_tw<C, 0>(tw.data(), tid), (Word)p, np, twop, ninv);
-      for (int k = 0; k < C::E; ++k) data[pass_pos<C, 0>(tid, k)] = (uint64_t)x[k];
+      window_store<C>(x, slab.data(), tid);
     }
+    for (int i = 0; i < C::N; ++i) data[i] = (uint64_t)slab[i];
   }
   return 0;
 }

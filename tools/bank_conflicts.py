@@ -40,7 +40,7 @@ def wavefronts(word_addrs, words_per_access):
     return total, words_per_access
 
 
-def analyse(wb, n, swz=False, tile_log=None):
+def analyse(wb, n, swz=False, adj=True):
     e, npass, r, s0, hi, c = plan(n, wb)
     E = 1 << e
     wsz = wb // 32                     # 4-byte words per element
@@ -55,7 +55,15 @@ def analyse(wb, n, swz=False, tile_log=None):
         tot = mn = 0
         for w0 in range(0, tpu, 32):
             lanes = [w0 + l for l in range(min(32, tpu))]
-            if c[i] == 0:  # row per thread, 16-byte vectors
+            cb = e - r[0] if (wb == 64 and i == 0 and adj) else 0
+            cb = cb if (cb == 1 and n == 14) else 0  # NttCfg::CB (the shipped default)
+            if cb >= 1:  # pass 0 with adjacent columns (NttCfg::ADJ): 2^cb consecutive words per butterfly index, 16-byte vectors
+                for kh in range(1 << r[0]):
+                    for v in range((1 << cb) // vec):
+                        addrs = [A((kh << (n - r[0])) | (t << cb) | (v * vec)) * wsz for t in lanes]
+                        wf, m = wavefronts(addrs + [addrs[0]] * (32 - len(addrs)), 4)
+                        tot += wf; mn += m
+            elif c[i] == 0:  # row per thread, 16-byte vectors
                 for v in range(E // vec):
                     addrs = [A(t * E + v * vec) * wsz for t in lanes]
                     wf, m = wavefronts(addrs + [addrs[0]] * (32 - len(addrs)), 4)
