@@ -154,7 +154,17 @@ template <int LB, int LOGN> struct NttCfg {
 #endif
   static constexpr bool ADJ = CB >= 1;
   static constexpr size_t SCHED_BYTES = DYNAMIC ? (((size_t)2 * SLOTS * sizeof(uint32_t) + 15) & ~(size_t)15) : 0;
-  static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES;
+  // Experiment (-DNFLGPU_TMA_SLAB, north_star's "coefficients staged into shared memory via TMA"; statically walked single-tile shapes):
+  // one elected thread per unit slot brings the next unit's slab into the slot's tile with a bulk copy (cp.async.bulk + mbarrier) as
+  // soon as the copy-out has released the tile, and pass 0 reads its window from shared memory instead of global memory.  Measured on
+  // B200 for N = 1024 x 64-bit: profiles/r02_variants.log block 10.  Not in the shipped build.
+#ifdef NFLGPU_TMA_SLAB
+  static constexpr bool TMA_SLAB = SPLIT == 0 && !DYNAMIC && NP > 1 && sizeof(Store) == sizeof(Word) && !ADJ;
+#else
+  static constexpr bool TMA_SLAB = false;
+#endif
+  static constexpr size_t SLAB_BAR_BYTES = TMA_SLAB ? (((size_t)SLOTS * 8 + 15) & ~(size_t)15) : 0;
+  static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES + SLAB_BAR_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
   // tile address of a position (only its offset inside the sub-block matters)
   static NFLGPU_DEVFN int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
@@ -723,6 +733,44 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const TW *tw = stage_twiddles<C>(a, cm, smem);
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
   UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base, hop > 0);
+  if constexpr (C::TMA_SLAB) {  // experiment build only (NttCfg::TMA_SLAB)
+    unsigned char *sbar = smem + C::TW_BYTES + 16 + C::SCHED_BYTES + (size_t)slot * 8;
+    auto slab_of = [&](uint32_t j) { return src + ((size_t)j * a.nmoduli + cm) * C::N; };
+    auto fetch = [&](uint32_t j) {  // elected thread: the slot's tile <- slab j
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tile's earlier generic-proxy accesses come first
+      mbar_expect_tx(sbar, (uint32_t)(C::N * sizeof(Word)));
+      tma_load_1d(tile, slab_of(j), (uint32_t)(C::N * sizeof(Word)), sbar);
+    };
+    if (tl == 0) {
+      mbar_init(sbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unit_sync<C>(slot, lane_base);
+    if (tl == 0 && walk.index() < nblocks) fetch(walk.index());
+    uint32_t phase = 0;
+    for (; walk.index() < nblocks; walk.advance()) {
+      const uint32_t j = walk.index();
+      const size_t ubase = ((size_t)j * a.nmoduli + cm) * C::N;
+      const int tid = tl;
+      next_unit_prefetch<C>(walk, src, a.nmoduli, cm, nblocks, tl);  // L2, one unit ahead of the bulk copy
+      Word x[C::E];
+      mbar_wait(sbar, phase);
+      phase ^= 1;
+#pragma unroll
+      for (int k = 0; k < C::E; ++k) x[k] = tile[pass_pos<C, S>(tid, k)];  // dense slab image: lane-contiguous, conflict free
+      unit_sync<C>(slot, lane_base);  // everybody holds its window: the padded layout may overwrite the image
+      fwd_pass<C, S>(x, pass_tw<C, S>(tw, tid), np, twop);
+      tile_store<C, S>(x, tile, tid);
+      unit_sync<C>(slot, lane_base);
+      FwdChain<C, S + 1>::run(x, tile, tw, p, np, twop, tid, slot, lane_base);
+      unit_sync<C>(slot, lane_base);
+      if (MUL) tile_to_gmem_mul<C, LB>(tile, dst + ubase, reinterpret_cast<const Store *>(a.other) + ubase, tl, p, a.consts[cm]);
+      else tile_to_gmem<C>(tile, dst + ubase, tl);
+      unit_sync<C>(slot, lane_base);  // the copy-out has released the tile
+      const uint32_t jn = walk.peek_next();
+      if (tl == 0 && jn < nblocks) fetch(jn);
+    }
+  } else {
   Word x[C::E];
   // pass-0 window of sub-block j, straight from global memory: for fixed k the threads touch consecutive limbs
   auto load_window = [&](uint32_t j) {
@@ -773,6 +821,7 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
 #endif
     }
   }
+  }  // (regular path)
   }  // hop
 #ifdef NFLGPU_TRACE
   if (tl == 0 && blockIdx.x * C::SLOTS + slot < 8192) nflgpu_trace_buf[1 + blockIdx.x * C::SLOTS + slot] = trace_now();
