@@ -94,6 +94,7 @@ int main(int argc, char **argv) {
   bad |= run(32, 4096, 2, 1500, launches / 8 + 1);
   bad |= run(64, 4096, 2, 500, launches / 8 + 1);
   bad |= run(64, 8192, 1, 700, launches / 8 + 1);
+  bad |= run(64, 16384, 1, 300, launches / 8 + 1);  // 128-bit pass-0 window (NttCfg::ADJ) + pipelined inverse
   bad |= run_host(64, 1024, 4, 2600);
   bad |= run(64, 2048, 3, 37, launches);     // dynamic unit walk, two-pass tile
   bad |= run(64, 2048, 3, 1, launches);

@@ -473,3 +473,48 @@ def test_cluster_transforms_with_more_units_than_clusters(n, M, batch):
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.split() == [sha(fa), sha(ia)]
     c.close()
+
+
+# ---- CUDA graphs ---------------------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("bits,N,M,batch", [(64, 1024, 4, 8), (32, 4096, 3, 5), (64, 2048, 2, 3)])
+def test_transform_chain_is_capturable_in_a_cuda_graph(bits, N, M, batch):
+    """The launches are plain stream-ordered kernel launches, so a small-batch chain -- forward(a), forward(b), product, inverse:
+    the four calls of tests/nfllib_demo_main_op.cpp:31-45 -- can be captured once and replayed (launch-bound inner loops).  The
+    dynamically scheduled sizes need one eager call on the capture stream first (their per-stream counter set is created then);
+    replays on new operand values are bit-identical to the oracle's negacyclic product."""
+    import torch
+    c, o = nb.Context(bits, N, M), Oracle(bits, N, M)
+    view = {32: np.int32, 64: np.int64}[bits]
+    a0, b0 = random_polys(bits, N, M, batch, 4101), random_polys(bits, N, M, batch, 4102)
+    a1, b1 = random_polys(bits, N, M, batch, 4103), random_polys(bits, N, M, batch, 4104)
+    da, db = torch.from_numpy(a0.view(view)).cuda(), torch.from_numpy(b0.view(view)).cuda()
+    fa, fb, out = torch.empty_like(da), torch.empty_like(da), torch.empty_like(da)
+    s = torch.cuda.Stream()
+
+    def chain(sh):
+        c.ntt_fwd(fa.data_ptr(), da.data_ptr(), batch, sh)
+        c.ntt_fwd(fb.data_ptr(), db.data_ptr(), batch, sh)
+        c.mul(fa.data_ptr(), fa.data_ptr(), fb.data_ptr(), batch, sh)
+        c.ntt_inv(out.data_ptr(), fa.data_ptr(), batch, sh)
+
+    with torch.cuda.stream(s):
+        chain(s.cuda_stream)  # eager: function attributes, counter sets
+    s.synchronize()
+    want0 = o.run("polymul", a0, b0)
+    assert np.array_equal(out.cpu().numpy().view(a0.dtype), want0)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        chain(torch.cuda.current_stream().cuda_stream)
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(a0.dtype), want0)
+    da.copy_(torch.from_numpy(a1.view(view)))
+    db.copy_(torch.from_numpy(b1.view(view)))
+    for _ in range(3):  # replays back to back: the dynamic walk's counters are re-armed by every launch
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy().view(a0.dtype), o.run("polymul", a1, b1))
+    c.close()
