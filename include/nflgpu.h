@@ -266,8 +266,9 @@ int nflgpu_host_op(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, 
 /* The same call without the final wait: it returns once the last chunk has been queued (it only blocks while the ring is
  * full), so a caller that streams several independent batches keeps the uploads of the next call running under the
  * downloads of this one.  Operands and destination must stay valid and untouched until nflgpu_host_sync (or any
- * nflgpu_host_op on the same context) has returned; only then is dst complete.  An error reported by a later call or by
- * nflgpu_host_sync may belong to an earlier asynchronous call. */
+ * nflgpu_host_op on the same context) has returned; only then is dst complete -- in particular the destination of one
+ * asynchronous call cannot be an operand of another before that (the calls in flight are independent batches).  An error
+ * reported by a later call or by nflgpu_host_sync may belong to an earlier asynchronous call. */
 int nflgpu_host_op_async(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, const void *b_host,
                          const void *c_host, size_t batch);
 int nflgpu_host_sync(nflgpu_ctx *ctx);

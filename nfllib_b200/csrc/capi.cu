@@ -1100,8 +1100,9 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
   if (!g.ok) { set_error("cannot select CUDA device"); return NFLGPU_ERR_CUDA; }
   HostPipe &p = ctx->pipe;
   if (batch == 0) return wait ? host_drain(ctx) : NFLGPU_OK;
-  if (!p.run) {
-    for (cudaStream_t *st : {&p.in, &p.run, &p.out}) CUDA_TRY(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
+  if (!p.out) {  // (`out` is created last: a failure half way is retried by the next call)
+    for (cudaStream_t *st : {&p.in, &p.run, &p.out})
+      if (!*st) CUDA_TRY(cudaStreamCreateWithFlags(st, cudaStreamNonBlocking));
   }
   const size_t poly_bytes = ctx->nmoduli * ctx->degree * ctx->limb_bytes;
   bool pinned[4] = {is_pinned(a_host), nin >= 2 && is_pinned(b_host), nin >= 3 && is_pinned(c_host), is_pinned(dst_host)};
