@@ -71,3 +71,28 @@ def test_32_bit_butterflies_use_the_min_based_conditional_subtract():
     ops = sass(FWD12_32)
     assert any(o.startswith("VIADDMNMX.U32") for o in ops)
     assert sum(o.startswith("IMAD.HI") for o in ops) <= 4  # prologue division only: the butterflies' high product is an IMAD.WIDE
+
+
+INV12_32 = "_ZN6nflgpu14ntt_inv_kernelILi32ELi12EEEvNS_7NttArgsE"
+INV13 = "_ZN6nflgpu14ntt_inv_kernelILi64ELi13EEEvNS_7NttArgsE"
+FWD14 = "_ZN6nflgpu14ntt_fwd_kernelILi64ELi14ELb0EEEvNS_7NttArgsE"
+INV14 = "_ZN6nflgpu14ntt_inv_kernelILi64ELi14EEEvNS_7NttArgsE"
+CLFWD15 = "_ZN6nflgpu22ntt_cluster_fwd_kernelILi64ELi15ELb0EEEvNS_11ClusterArgsE"
+
+
+def test_round2_mechanisms_are_in_the_binary():
+    """Round-2 claims of DESIGN §4.1 read back from the SASS: the pipelined inverse kernels copy the next unit in with cp.async (LDGSTS)
+    from N = 4096 up and not for N = 1024; the N = 16384 shape moves its pass-0 window as 16-byte vectors in both directions; the
+    N = 2^15 cluster kernel scatters through distributed shared memory; the C4 kernels still fit four CTAs per SM (64 registers)."""
+    for k in (INV12_32, INV13, INV14):
+        assert any(o.startswith("LDGSTS") for o in sass(k)), f"{k}: cp.async copy-in of the next unit missing"
+    assert not any(o.startswith("LDGSTS") for o in sass(INV10))
+    assert sum(o.startswith("LDG.E.128.CONSTANT") for o in sass(FWD14)) >= 16, "N = 16384 forward: pass-0 window no longer loaded as 16-byte vectors"
+    assert sum(o.startswith("STG.E.128") for o in sass(INV14)) >= 16, "N = 16384 inverse: pass-0 window no longer stored as 16-byte vectors"
+    assert not any(o.startswith("LDG.E.128.CONSTANT") for o in sass(FWD10)), "N = 1024 keeps 8-byte column loads (measured faster)"
+    cl = sass(CLFWD15)
+    assert any(o.startswith("UCGABAR_ARV") for o in cl) and any(o.startswith("UCGABAR_WAIT") for o in cl), "cluster barrier missing"
+    assert sum(o.startswith("ST.E.64") for o in cl) >= 16, "pass-0 scatter into the partner CTA's tile (st.shared::cluster) missing"
+    r = resources()
+    for k in (FWD12_32, INV12_32):
+        assert r[k]["reg"] <= 64 and r[k]["stack"] == 0, (k, r[k])
