@@ -143,7 +143,19 @@ __global__ void __launch_bounds__(ClusterCfg<LB, LOGN>::THREADS, 1) ntt_cluster_
   for (int r = 0; r < C::CL; ++r) cbase[r] = mapa_u32(smem_u32(tiles + C::pad(t0)), (uint32_t)r);
 
   const uint32_t units = a.batch * a.nmoduli;
+  // Experiment (-DNFLGPU_PIPE=1), pipelining across units like ntt_inv_kernel (NttCfg::PIPE_INV): this CTA's sub-blocks of the NEXT unit are
+  // copied into the tiles with cp.async as soon as every CTA of the cluster has gathered its pass-0 window out of them, and land while
+  // pass 0 computes and stores.  Measured on B200 (profiles/r02_variants.log block 11): 217.4 vs 216.6 us (M = 2, batch 256), 833.6 vs
+  // 824.8 us (M = 4, batch 512) -- no gain, the cluster barrier moved in front of pass 0 costs what the hidden copy saves; off by default.
+#if defined(NFLGPU_PIPE) && NFLGPU_PIPE == 1
+  constexpr bool PIPE = sizeof(Store) == sizeof(Word);
+#else
+  constexpr bool PIPE = false;
+#endif
   cluster.sync();  // every CTA of the cluster is running (its shared memory exists) before the first remote access
+  if constexpr (PIPE) {
+    if (cid < units) gmem_to_tile_async<C>(tile, src + (size_t)cid * C::N + (size_t)sub * C::B, tl);
+  }
   for (uint32_t u = cid; u < units; u += a.nclusters) {
     const uint32_t cm = u % a.nmoduli;
     const size_t ubase = (size_t)u * C::N;
@@ -151,7 +163,8 @@ __global__ void __launch_bounds__(ClusterCfg<LB, LOGN>::THREADS, 1) ntt_cluster_
     const TW ninv = __ldg(tw + C::N - 1);
     const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
     Word x[C::E];
-    gmem_to_tile<C>(tile, src + ubase + (size_t)sub * C::B, tl);
+    if constexpr (PIPE) cp_async_wait();
+    else gmem_to_tile<C>(tile, src + ubase + (size_t)sub * C::B, tl);
     unit_sync<C>(slot, lane_base);
     InvChain<C, C::NP - 1>::run(x, tile, tw, p, np, twop, ninv, tid, slot, lane_base);  // passes NP-1 .. 2, tile -> tile
     unit_sync<C>(slot, lane_base);
@@ -161,10 +174,15 @@ __global__ void __launch_bounds__(ClusterCfg<LB, LOGN>::THREADS, 1) ntt_cluster_
     cluster.sync();  // every sub-block of the unit has finished its tile passes
 #pragma unroll
     for (int k = 0; k < C::E; ++k) ld_cluster(cbase[k / C::TPC] + (uint32_t)((k % C::TPC) * C::TILE_WORDS * sizeof(Word)), x[k]);
+    if constexpr (PIPE) {
+      cluster.sync();  // all gathers are done: the tiles are free for the next unit
+      const uint32_t un = u + a.nclusters;
+      if (un < units) gmem_to_tile_async<C>(tile, src + (size_t)un * C::N + (size_t)sub * C::B, tl);
+    }
     inv_pass<C, 0>(x, pass_tw<C, 0>(tw, t0), p, np, twop, ninv);
 #pragma unroll
     for (int k = 0; k < C::E; ++k) dst[ubase + pass_pos<C, 0>(t0, k)] = (Store)x[k];
-    cluster.sync();  // all gathers are done before the next unit overwrites the tiles
+    if constexpr (!PIPE) cluster.sync();  // all gathers are done before the next unit overwrites the tiles
   }
 }
 

@@ -90,6 +90,10 @@ static int run_host(int bits, size_t N, size_t M, size_t batch) {
 int main(int argc, char **argv) {
   const int launches = argc > 1 ? std::atoi(argv[1]) : 300;
   int bad = 0;
+  if (argc > 2 && std::atoi(argv[2]) == 32768) {  // only the cluster kernels, with several units per cluster (pipelined inverse)
+    bad |= run(64, 32768, 2, 200, launches / 4 + 1);
+    return bad;
+  }
   // more units than unit slots: the software-pipelined kernels (ntt_engine.cuh PIPE_INV / PIPE_FWD) prefetch their next unit
   bad |= run(32, 4096, 2, 1500, launches / 8 + 1);
   bad |= run(64, 4096, 2, 500, launches / 8 + 1);
