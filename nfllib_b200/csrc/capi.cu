@@ -1170,6 +1170,13 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
   } while (0)
   // a call that fits one chunk has nothing to overlap: all three steps go on one stream (no event hops on the latency path)
   const bool single = batch <= chunk;
+  // ... and a SMALL one (a single host poly, what poly::ntt_pow_phi() is) skips the copy engines altogether: the kernel reads its
+  // operands from, and writes its result to, mapped pinned memory over PCIe -- one launch and one wait instead of upload, launch,
+  // download and wait (measured: profiles/r02_variants.log block 12).  NFLGPU_HOST_SMALL_KIB sets the limit (0 = never).
+  static const size_t small_bytes = (size_t)env_long("NFLGPU_HOST_SMALL_KIB", 0, 65536, 128) << 10;
+  bool direct = single && batch * poly_bytes <= small_bytes;
+  for (int i = 0; i < nin; ++i) direct = direct && (!pinned[i] || (reinterpret_cast<uintptr_t>(in[i]) & 15) == 0);  // (kernels want 16-byte alignment;
+  direct = direct && (!pinned[3] || (reinterpret_cast<uintptr_t>(dst_host) & 15) == 0);                              //  the copy engines do not care)
   cudaStream_t sin = single ? p.run : p.in, sout = single ? p.run : p.out;
   for (size_t done = 0; done < batch;) {
     HostSlot &s = p.slot[p.next];
@@ -1177,6 +1184,7 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
     if (rc != NFLGPU_OK) { host_abort(ctx); return rc; }
     const size_t cnt = (batch - done < chunk) ? batch - done : chunk;
     const size_t bytes = cnt * poly_bytes;
+    void *kd[4] = {s.dev[0], s.dev[1], s.dev[2], s.dev[3]};  // what the kernels read and write
     for (int i = 0; i < nin; ++i) {
       const char *src = static_cast<const char *>(in[i]) + done * poly_bytes;
       if (!pinned[i]) {
@@ -1184,8 +1192,15 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
         staging_copy(s.pin[i], src, bytes);
         src = static_cast<const char *>(s.pin[i]);
       }
-      PIPE_TRY(cudaMemcpyAsync(s.dev[i], src, bytes, cudaMemcpyHostToDevice, sin));
+      if (direct) PIPE_TRY(cudaHostGetDevicePointer(&kd[i], const_cast<char *>(src), 0));
+      else PIPE_TRY(cudaMemcpyAsync(s.dev[i], src, bytes, cudaMemcpyHostToDevice, sin));
     }
+    char *user = static_cast<char *>(dst_host) + done * poly_bytes, *out = user;
+    if (!pinned[3]) {
+      if (!s.pin[3]) PIPE_TRY(cudaHostAlloc(&s.pin[3], p.slot_bytes, cudaHostAllocDefault));
+      out = static_cast<char *>(s.pin[3]);
+    }
+    if (direct) PIPE_TRY(cudaHostGetDevicePointer(&kd[3], out, 0));
     if (!single) {
       PIPE_TRY(cudaEventRecord(s.up, sin));
       PIPE_TRY(cudaStreamWaitEvent(p.run, s.up, 0));
@@ -1193,19 +1208,14 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
 #ifdef NFLGPU_HOST_NOKERNEL  // timing experiment (tools/e2e_sweep.py): copies and events only, results are wrong
     rc = NFLGPU_OK;
 #else
-    rc = host_dispatch(ctx, op, s.dev, cnt, p.run);
+    rc = host_dispatch(ctx, op, kd, cnt, p.run);
 #endif
     if (rc != NFLGPU_OK) { host_abort(ctx); return rc; }
     if (!single) {
       PIPE_TRY(cudaEventRecord(s.done, p.run));
       PIPE_TRY(cudaStreamWaitEvent(sout, s.done, 0));
     }
-    char *user = static_cast<char *>(dst_host) + done * poly_bytes, *out = user;
-    if (!pinned[3]) {
-      if (!s.pin[3]) PIPE_TRY(cudaHostAlloc(&s.pin[3], p.slot_bytes, cudaHostAllocDefault));
-      out = static_cast<char *>(s.pin[3]);
-    }
-    PIPE_TRY(cudaMemcpyAsync(out, s.dev[3], bytes, cudaMemcpyDeviceToHost, sout));
+    if (!direct) PIPE_TRY(cudaMemcpyAsync(out, s.dev[3], bytes, cudaMemcpyDeviceToHost, sout));
     PIPE_TRY(cudaEventRecord(s.down, sout));
     s.busy = true;
     s.unstage_to = pinned[3] ? nullptr : user;
