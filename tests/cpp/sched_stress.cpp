@@ -81,7 +81,14 @@ static int run_host(int bits, size_t N, size_t M, size_t batch) {
   CHECK(nflgpu_host_op_async(ctx, 1, ra.data(), fa.data(), nullptr, nullptr, batch));
   CHECK(nflgpu_host_op_async(ctx, 1, rc.data(), fc.data(), nullptr, nullptr, batch));
   CHECK(nflgpu_host_op(ctx, 1, fc.data(), fc.data(), nullptr, nullptr, batch));  // blocking, in place, behind the asynchronous ones
-  const int bad = std::memcmp(ra.data(), a.data(), bytes) != 0 || std::memcmp(rc.data(), c.data(), bytes) != 0 || std::memcmp(fc.data(), c.data(), bytes) != 0;
+  int bad = std::memcmp(ra.data(), a.data(), bytes) != 0 || std::memcmp(rc.data(), c.data(), bytes) != 0 || std::memcmp(fc.data(), c.data(), bytes) != 0;
+  // one polynomial: the small-call path (the kernel reads and writes mapped pinned memory), forward then inverse in place
+  const size_t one = nflgpu_batch_bytes(ctx, 1);
+  std::vector<unsigned char> x(a.begin() + one, a.begin() + 2 * one);
+  CHECK(nflgpu_host_op(ctx, 0, x.data(), x.data(), nullptr, nullptr, 1));
+  bad |= std::memcmp(x.data(), fa.data() + one, one) != 0;
+  CHECK(nflgpu_host_op(ctx, 1, x.data(), x.data(), nullptr, nullptr, 1));
+  bad |= std::memcmp(x.data(), a.data() + one, one) != 0;
   std::printf("u%d N=%zu M=%zu batch=%zu: host ring, 2 x (fwd, inv) asynchronous + 1 blocking in place: %s\n", bits, N, M, batch, bad ? "MISMATCH" : "ok");
   nflgpu_ctx_destroy(ctx);
   return bad;
