@@ -193,6 +193,12 @@ def test_host_op_async_ring_matches_blocking_calls():
         c.host_op("inv", y, out=y, wait=False)
         c.host_sync()
         assert np.array_equal(y, a)
+        # one page-locked polynomial, in place: the small-call path (the kernel reads and writes the mapped host memory itself)
+        c.host_op("fwd", y[7:8], out=y[7:8])
+        assert np.array_equal(y[7:8], fa[7:8]) and np.array_equal(y[:7], a[:7]) and np.array_equal(y[8:], a[8:])
+        c.host_op("inv", y[7:8], out=y[7:8])
+        assert np.array_equal(y, a)
+        assert np.array_equal(c.host_op("polymul", y[3:4], b[3:4]), o.run("polymul", a[3:4], b[3:4]))  # pinned + pageable operands
     finally:
         c.host_unregister(y)
     c.host_sync()  # nothing in flight: returns at once
