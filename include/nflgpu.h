@@ -256,8 +256,8 @@ int nflgpu_poly2mpz_slabs(nflgpu_ctx *ctx, uint64_t *dst_words, const void *cons
 /* ---- host-buffer entry points (what a single host nfl::poly call maps to) -------------------------------- *
  * Same operations on HOST buffers: host->device copy, kernel(s), device->host copy, cut into chunks that move through a
  * ring of device buffers on three streams (uploads / kernels / downloads, chained by events), so both PCIe directions
- * and the kernels overlap; a small call (one chunk, <= NFLGPU_HOST_SMALL_KIB = 128 KiB per operand) lets the kernel read and write
- * mapped pinned memory directly instead (latency path of a single polynomial).  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,
+ * and the kernels overlap; a small call (one chunk, <= NFLGPU_HOST_SMALL_KIB = 8 MiB per operand) lets the kernel read and write
+ * mapped pinned memory directly instead (the latency path: a single polynomial, a few hundred at most).  op: 0 fwd, 1 inv, 2 mul, 3 mul_shoup, 4 compute_shoup, 5 add,
  * 6 sub, 8 polymul, 9 muladd, 10 raw_fwd (core::ntt), 11 raw_inv (core::inv_ntt).  Unused operands are NULL.  dst may be
  * one of the operands (in place).  These are the calls bench.py's e2e figure times.
  * Not re-entrant per context (the ring belongs to the context): serialise calls on one context, or use

@@ -1172,8 +1172,10 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
   const bool single = batch <= chunk;
   // ... and a SMALL one (a single host poly, what poly::ntt_pow_phi() is) skips the copy engines altogether: the kernel reads its
   // operands from, and writes its result to, mapped pinned memory over PCIe -- one launch and one wait instead of upload, launch,
-  // download and wait (measured: profiles/r02_variants.log block 12).  NFLGPU_HOST_SMALL_KIB sets the limit (0 = never).
-  static const size_t small_bytes = (size_t)env_long("NFLGPU_HOST_SMALL_KIB", 0, 65536, 128) << 10;
+  // download and wait.  Measured (profiles/r02_variants.log blocks 12, 13): faster than the copy engines for every one-chunk size tried,
+  // 32 KiB (26 vs 33 us) to 8 MiB (306 vs 353+ us) -- a lone chunk cannot overlap its upload with its download, the kernel's own
+  // reads and writes do.  NFLGPU_HOST_SMALL_KIB sets the limit per operand (default 8 MiB, 0 = never).
+  static const size_t small_bytes = (size_t)env_long("NFLGPU_HOST_SMALL_KIB", 0, 65536, 8192) << 10;
   bool direct = single && batch * poly_bytes <= small_bytes;
   for (int i = 0; i < nin; ++i) direct = direct && (!pinned[i] || (reinterpret_cast<uintptr_t>(in[i]) & 15) == 0);  // (kernels want 16-byte alignment;
   direct = direct && (!pinned[3] || (reinterpret_cast<uintptr_t>(dst_host) & 15) == 0);                              //  the copy engines do not care)
