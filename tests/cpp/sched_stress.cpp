@@ -14,6 +14,7 @@
 #define CHECK(x) do { int rc_ = (x); if (rc_ != 0) { std::fprintf(stderr, "%s -> %d (%s)\n", #x, rc_, nflgpu_last_error()); return 1; } } while (0)
 
 static int run(int bits, size_t N, size_t M, size_t batch, int launches) {
+  if (launches < 2) launches = 2;  // both streams must have produced a result before they are compared
   nflgpu_ctx *ctx = nullptr;
   CHECK(nflgpu_ctx_create(&ctx, bits, N, M, 0, 0, nullptr, nullptr));
   std::vector<uint64_t> P(M);
