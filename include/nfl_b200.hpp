@@ -812,7 +812,7 @@ template <class T, size_t D, size_t M> std::ostream &operator<<(std::ostream &os
 // ---------------------------------------------------------------------------------------------------------
 namespace cuda {
 
-// Whole host arrays of polys through the chunked, double-buffered host pipeline (nflgpu_host_op): what a loop of
+// Whole host arrays of polys through the chunked host-buffer ring (nflgpu_host_op: upload, kernel and download of neighbouring chunks overlap): what a loop of
 // p[i].ntt_pow_phi() over a contiguous array should be written as.  In place.
 template <class P> void ntt_pow_phi(P *polys, size_t count) {
   detail::check(nflgpu_host_op(P::backend_type::get().ctx, 0, polys, polys, nullptr, nullptr, count), "ntt_pow_phi[]");
