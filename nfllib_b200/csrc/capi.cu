@@ -1176,7 +1176,8 @@ int host_pipeline(nflgpu_ctx *ctx, int op, void *dst_host, const void *a_host, c
   // 32 KiB (26 vs 33 us) to 8 MiB (306 vs 353+ us) -- a lone chunk cannot overlap its upload with its download, the kernel's own
   // reads and writes do.  NFLGPU_HOST_SMALL_KIB sets the limit per operand (default 8 MiB, 0 = never).
   static const size_t small_bytes = (size_t)env_long("NFLGPU_HOST_SMALL_KIB", 0, 65536, 8192) << 10;
-  bool direct = single && batch * poly_bytes <= small_bytes;
+  // (not for the split transforms, N > 2^15: their global-memory passes work in place on the destination several times)
+  bool direct = single && batch * poly_bytes <= small_bytes && ctx->log2_degree <= 15;
   for (int i = 0; i < nin; ++i) direct = direct && (!pinned[i] || (reinterpret_cast<uintptr_t>(in[i]) & 15) == 0);  // (kernels want 16-byte alignment;
   direct = direct && (!pinned[3] || (reinterpret_cast<uintptr_t>(dst_host) & 15) == 0);                              //  the copy engines do not care)
   cudaStream_t sin = single ? p.run : p.in, sout = single ? p.run : p.out;
