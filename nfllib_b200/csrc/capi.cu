@@ -5,6 +5,7 @@
 #include "gaussian.h"
 #include "lift.h"
 #include "ntt_dispatch.h"
+#include "ntt_plan.h"
 #include "pointwise.h"
 
 #include <atomic>
@@ -117,19 +118,27 @@ namespace {
 int upload_tables(nflgpu_ctx *ctx, bool raw, void **d_fwd, void **d_inv) {
   const int word_bits = ctx->limb_bits == 64 ? 64 : 32;
   const size_t tw_entry = ctx->limb_bits == 64 ? 16 : 8, degree = ctx->degree, nmoduli = ctx->nmoduli;
-  std::vector<unsigned char> hf(nmoduli * degree * tw_entry), hi(nmoduli * degree * tw_entry);
+  const size_t inv_entries = (size_t)plan_inv_entries((int)ctx->log2_degree, word_bits);  // N + N/2 when N^-1 is folded into the twiddles
+  std::vector<unsigned char> hf(nmoduli * degree * tw_entry), hi(nmoduli * inv_entries * tw_entry);
   for (size_t cm = 0; cm < nmoduli; ++cm) {
     ResidueTables t;
     build_residue_tables(ctx->limb_bits, word_bits, degree, ctx->moduli[cm], ctx->roots[cm], ctx->kmax, &t, raw);
     for (size_t i = 0; i < degree; ++i) {
       if (word_bits == 64) {
         uint64_t *f = reinterpret_cast<uint64_t *>(hf.data()) + (cm * degree + i) * 2;
-        uint64_t *v = reinterpret_cast<uint64_t *>(hi.data()) + (cm * degree + i) * 2;
-        f[0] = t.fwd_w[i]; f[1] = t.fwd_ws[i]; v[0] = t.inv_w[i]; v[1] = t.inv_ws[i];
+        f[0] = t.fwd_w[i]; f[1] = t.fwd_ws[i];
       } else {
         uint32_t *f = reinterpret_cast<uint32_t *>(hf.data()) + (cm * degree + i) * 2;
-        uint32_t *v = reinterpret_cast<uint32_t *>(hi.data()) + (cm * degree + i) * 2;
-        f[0] = (uint32_t)t.fwd_w[i]; f[1] = (uint32_t)t.fwd_ws[i]; v[0] = (uint32_t)t.inv_w[i]; v[1] = (uint32_t)t.inv_ws[i];
+        f[0] = (uint32_t)t.fwd_w[i]; f[1] = (uint32_t)t.fwd_ws[i];
+      }
+    }
+    for (size_t i = 0; i < inv_entries; ++i) {
+      if (word_bits == 64) {
+        uint64_t *v = reinterpret_cast<uint64_t *>(hi.data()) + (cm * inv_entries + i) * 2;
+        v[0] = t.inv_w[i]; v[1] = t.inv_ws[i];
+      } else {
+        uint32_t *v = reinterpret_cast<uint32_t *>(hi.data()) + (cm * inv_entries + i) * 2;
+        v[0] = (uint32_t)t.inv_w[i]; v[1] = (uint32_t)t.inv_ws[i];
       }
     }
   }

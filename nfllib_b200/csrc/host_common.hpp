@@ -25,7 +25,7 @@ uint64_t invmod64(uint64_t a, uint64_t p);
 // to uint64_t (the uploader narrows them to the kernel's word type).
 struct ResidueTables {
   std::vector<uint64_t> fwd_w, fwd_ws;  // N entries each
-  std::vector<uint64_t> inv_w, inv_ws;  // N entries each; [N-1] = N^-1, entry of stage 0 pre-multiplied by N^-1
+  std::vector<uint64_t> inv_w, inv_ws;  // plan_inv_entries() each (ntt_plan.h: N, or N + N/2 when N^-1 is folded into the twiddles); [N-1] = N^-1
 };
 // limb_bits: 16/32/64 (Shoup shift); word_bits: 32 or 64 (kernel word: 16-bit limbs compute in 32-bit words)
 // raw = true builds the tables of the cyclic transform core::ntt / core::inv_ntt (no phi twist, no N^-1)

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(ClusterCfg<LB, LOGN>::THREADS, 1) ntt_cluster_
   for (uint32_t u = cid; u < units; u += a.nclusters) {
     const uint32_t cm = u % a.nmoduli;
     const size_t ubase = (size_t)u * C::N;
-    const TW *tw = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::N;
+    const TW *tw = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::INV_TW;
     const TW ninv = __ldg(tw + C::N - 1);
     const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
     Word x[C::E];

@@ -166,6 +166,13 @@ template <int LB, int LOGN> struct NttCfg {
   static constexpr size_t SLAB_BAR_BYTES = TMA_SLAB ? (((size_t)SLOTS * 8 + 15) & ~(size_t)15) : 0;
   static constexpr size_t TILE_OFF = TW_BYTES + 16 /* mbarrier */ + SCHED_BYTES + SLAB_BAR_BYTES;
   static constexpr size_t SMEM_BYTES = TILE_OFF + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
+  // Inverse direction: N^-1 folded into the twiddles (ntt_plan.h plan_fold): N + N/2 table entries per residue, all of them staged
+  // into shared memory when the table is staged at all.
+  static constexpr bool FOLD = plan_fold(n, WB);
+  static constexpr int INV_TW = plan_inv_entries(n, WB);
+  static constexpr size_t TW_BYTES_INV = TW_SMEM ? (size_t)INV_TW * sizeof(TW) : 0;
+  static constexpr size_t TILE_OFF_INV = TW_BYTES_INV + 16 /* mbarrier */ + SCHED_BYTES;
+  static constexpr size_t SMEM_BYTES_INV = TILE_OFF_INV + (size_t)SLOTS * TILE_WORDS * sizeof(Word);
   // tile address of a position (only its offset inside the sub-block matters)
   static NFLGPU_DEVFN int pad(int pos) { return (pos & (B - 1)) + ((pos & (B - 1)) >> e) * PADW; }
   // the same for a compile-time position offset made of register-index bits only (below B by construction)
@@ -287,7 +294,11 @@ template <class C, int PASS> NFLGPU_DEVFN void fwd_pass(typename C::Word (&x)[C:
 }
 
 // Inverse pass PASS: stages s0+r-1 .. s0 (reverse order), Gentleman-Sande, values lazily kept in [0, 2p);
-// the very last stage (PASS 0, q 0) also multiplies by N^-1 and produces canonical values.
+// the very last stage (PASS 0, q 0) produces canonical values.  N^-1: with folded tables (C::FOLD, ntt_plan.h plan_fold) the first
+// pass to run (NP-1: the thread's window is the position's low e bits) takes the twiddle of every butterfly whose register-index
+// bits below the paired one are all zero from the N^-1-scaled copy -- a compile-time choice -- and multiplies x[0] by N^-1 at its
+// end, after which every coefficient of the unit carries the factor; otherwise the last stage multiplies every sum output by N^-1
+// (its difference twiddle is pre-scaled in the table).
 // (A top-bit variant of this direction -- sums held with the bias 2^63 - 2p so that "U + V >= 2p" is a sign bit -- was built
 // and measured on B200: same instruction count gain as the forward one, no time gain at any size; not kept.)
 template <class C, int PASS> NFLGPU_DEVFN void inv_pass(typename C::Word (&x)[C::E], const typename C::TW *tw,
@@ -296,6 +307,8 @@ template <class C, int PASS> NFLGPU_DEVFN void inv_pass(typename C::Word (&x)[C:
   typedef typename C::A A;
   typedef typename C::Word Word;
   constexpr int r = plan_r(C::n, C::WB, PASS), G = 1 << plan_s0(C::n, C::WB, PASS), e = C::e;
+  constexpr bool FIRST = C::FOLD && PASS == C::NP - 1;
+  const typename C::TW *twa = tw + (C::N - plan_off(C::n, C::WB, PASS));  // (FIRST only) the scaled copy of this pass's entries
 #pragma unroll
   for (int q = r - 1; q >= 0; --q) {
     const int bit = e - 1 - q;
@@ -303,17 +316,24 @@ template <class C, int PASS> NFLGPU_DEVFN void inv_pass(typename C::Word (&x)[C:
     for (int k = 0; k < C::E; ++k) {
       if (k & (1 << bit)) continue;
       const int eidx = (1 << q) - 1 + (k >> (e - q));
-      const typename C::TW t = tw[eidx * G];
+      // (the stage pairing bit 0 has the scaled values in the table proper: every butterfly of it qualifies)
+      const bool scaled = FIRST && bit != 0 && (k & ((1 << bit) - 1)) == 0;
+      const typename C::TW t = (scaled ? twa : tw)[eidx * G];
       const Word U = x[k], V = x[k | (1 << bit)];
       const Word D = A::mul_shoup_lazy(U - V + twop, A::tw_w(t), A::tw_ws(t), np);
       if (PASS == 0 && q == 0) {
-        x[k] = csub_lazy(A::mul_shoup_lazy(U + V, A::tw_w(ninv), A::tw_ws(ninv), np), p);
+        if (C::FOLD) x[k] = csub_lazy(csub_lazy(U + V, twop), p);
+        else x[k] = csub_lazy(A::mul_shoup_lazy(U + V, A::tw_w(ninv), A::tw_ws(ninv), np), p);
         x[k | (1 << bit)] = csub_lazy(D, p);
       } else {
         x[k] = csub_lazy(U + V, twop);
         x[k | (1 << bit)] = D;
       }
     }
+  }
+  if (FIRST) {  // the one coefficient of the window no difference branch has touched
+    x[0] = A::mul_shoup_lazy(x[0], A::tw_w(ninv), A::tw_ws(ninv), np);
+    if (PASS == 0) x[0] = csub_lazy(x[0], p);  // (one-pass transforms: this is also the last stage)
   }
 }
 
@@ -623,8 +643,8 @@ template <class C> struct UnitWalk {
     return v;
   }
   __device__ __forceinline__ UnitWalk(const NttArgs &a, unsigned char *smem, int cm, int rank, int slot_, int tl, int lane_base_,
-                                      bool rearm = false)
-      : cnt(a.sched + cm), box(reinterpret_cast<uint32_t *>(smem + C::TW_BYTES + 16) + slot_), ahead(0),
+                                      bool rearm = false, size_t tw_bytes = C::TW_BYTES)
+      : cnt(a.sched + cm), box(reinterpret_cast<uint32_t *>(smem + tw_bytes + 16) + slot_), ahead(0),
         cur((uint32_t)rank * C::SLOTS + slot_), stride(a.ctas_per_residue * C::SLOTS), par(0), slot(slot_), lane_base(lane_base_),
         leader(tl == 0) {
     if (C::DYNAMIC) {
@@ -689,20 +709,21 @@ static __device__ unsigned long long nflgpu_trace_buf[1 + 8192];
 __device__ __forceinline__ unsigned long long trace_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 
-template <class C> __device__ __forceinline__ const typename C::TW *stage_twiddles(const NttArgs &a, int cm, unsigned char *smem) {
+template <class C, bool INV = false> __device__ __forceinline__ const typename C::TW *stage_twiddles(const NttArgs &a, int cm, unsigned char *smem) {
   typedef typename C::TW TW;
-  const TW *twg = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::N;
+  constexpr size_t TWB = INV ? C::TW_BYTES_INV : C::TW_BYTES;
+  const TW *twg = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * (INV ? C::INV_TW : C::N);
   if (!C::TW_SMEM) return twg;
   TW *tws = reinterpret_cast<TW *>(smem);
-  void *bar = smem + C::TW_BYTES;
+  void *bar = smem + TWB;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, (uint32_t)C::TW_BYTES);
-    tma_load_1d(tws, twg, (uint32_t)C::TW_BYTES, bar);
+    mbar_expect_tx(bar, (uint32_t)TWB);
+    tma_load_1d(tws, twg, (uint32_t)TWB, bar);
   }
   mbar_wait(bar, 0);
   return tws;
@@ -840,16 +861,16 @@ __global__ void __launch_bounds__(NttCfg<LB, LOGN>::THREADS, NttCfg<LB, LOGN>::M
   const int cm0 = blockIdx.x % a.nmoduli, rank = blockIdx.x / a.nmoduli;
   const int slot = threadIdx.x / C::TPU, tl = threadIdx.x % C::TPU;
   const int lane_base = (threadIdx.x & 31) - (tl & 31);
-  Word *tile = reinterpret_cast<Word *>(smem + C::TILE_OFF) + (size_t)slot * C::TILE_WORDS;
+  Word *tile = reinterpret_cast<Word *>(smem + C::TILE_OFF_INV) + (size_t)slot * C::TILE_WORDS;
   const Store *src = reinterpret_cast<const Store *>(a.src);
   Store *dst = reinterpret_cast<Store *>(a.dst);
 
   const uint32_t nblocks = a.batch << C::LOGG;  // the launcher keeps batch << LOGG below 2^31
   const int cm = cm0;  // (the inverse kernels stay bound to their residue: see NttCfg::HOP)
-  const TW *tw = stage_twiddles<C>(a, cm, smem);
+  const TW *tw = stage_twiddles<C, true>(a, cm, smem);
   const TW ninv = tw[C::N - 1];
   const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
-  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base);
+  UnitWalk<C> walk(a, smem, cm, rank, slot, tl, lane_base, false, C::TW_BYTES_INV);
   auto slab_of = [&](uint32_t j) { return src + ((size_t)(j >> C::LOGG) * a.nmoduli + cm) * C::N + (size_t)(j & ((1u << C::LOGG) - 1)) * C::B; };
   if constexpr (C::PIPE_INV) {
     if (walk.index() < nblocks) gmem_to_tile_async<C>(tile, slab_of(walk.index()), tl);
@@ -908,7 +929,7 @@ __global__ void __launch_bounds__(256) ntt_gpass_kernel(const NttArgs a) {
     const uint64_t u = t >> LOGT;
     const int tid = (int)(t & ((1u << LOGT) - 1));
     const int cm = (int)(u % a.nmoduli);
-    const TW *tw = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * C::N;
+    const TW *tw = reinterpret_cast<const TW *>(a.tw) + (size_t)cm * (INV ? C::INV_TW : C::N);
     const Word p = reinterpret_cast<const Word *>(a.moduli)[cm], twop = 2 * p, np = opaque_neg(p);
     const size_t ubase = (size_t)u * C::N;
     Word x[C::E];

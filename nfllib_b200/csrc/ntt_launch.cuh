@@ -74,6 +74,7 @@ template <int LB, int LOGN, int MODE> bool launch_ntt_cluster(const NttLaunch &l
 // MODE: 0 forward, 1 inverse, 2 forward with the fused "* other" epilogue
 template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch &l, int device, int num_sms, cudaStream_t stream) {
   typedef NttCfg<LB, LOGN> C;
+  constexpr size_t SMEM = MODE == 1 ? C::SMEM_BYTES_INV : C::SMEM_BYTES;  // (the inverse kernel may stage a larger twiddle table)
   void (*kernel)(const NttArgs);
   if constexpr (MODE == 1) kernel = ntt_inv_kernel<LB, LOGN>;
   else if constexpr (MODE == 2) kernel = ntt_fwd_kernel<LB, LOGN, true>;
@@ -83,10 +84,10 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
   static int blocks_per_sm[64] = {0};
   if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
   if (blocks_per_sm[device] == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, C::THREADS, C::SMEM_BYTES);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, C::THREADS, SMEM);
     if (e != cudaSuccess) return e;
     blocks_per_sm[device] = occ > 0 ? occ : 1;
   }
@@ -131,7 +132,7 @@ template <int LB, int LOGN, int MODE> cudaError_t launch_ntt_one(const NttLaunch
     grid = need_all < resident ? (uint32_t)need_all : resident;
     if (grid == 0) grid = 1;
   }
-  kernel<<<grid, C::THREADS, C::SMEM_BYTES, stream>>>(a);
+  kernel<<<grid, C::THREADS, SMEM, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if constexpr (C::SPLIT > 0 && MODE == 1) {  // inverse: tile kernel (src -> dst), then global passes SPLIT-1 .. 0 in place
     if (e != cudaSuccess) return e;

@@ -71,5 +71,32 @@ NFLGPU_HD constexpr int plan_split(int n, int word_bits) {
   return s;
 }
 
+// Inverse transform, 64-bit words: N^-1 is folded into the twiddles instead of being applied by one extra Shoup multiplication per
+// butterfly of the last stage (N/2 multiplications per unit, 1 / (log2 N + 1) of all of them).  The inverse pairs position bits
+// 0, 1, .. n-1 in that order, and its first pass (NP-1) holds the low e position bits of a thread's coefficients in the register
+// index.  If, inside that pass, a coefficient carries the factor N^-1 exactly when its bits below the current one are not all
+// zero, both inputs of a butterfly agree, the sum output keeps the invariant for free and the difference output has to pick the
+// factor up only when those low bits ARE all zero -- there the butterfly uses the twiddle w * N^-1 instead of w, a compile-time
+// choice per register index.  After the pass only register 0 of every thread lacks the factor: one multiplication per thread
+// (N / E per unit instead of N / 2), and the remaining passes and the last stage work on scaled values with plain twiddles.
+// The inverse table of such a shape has N + N/2 entries per residue: [0, N) as before except that the stage pairing bit 0 (every
+// butterfly of it is a "low bits all zero" one) holds the scaled values and no entry is pre-multiplied for the last stage;
+// [N, N + N/2) = the entries of pass NP-1's other stages times N^-1, in the same [e_idx][g] order.  (32-bit words keep the extra
+// multiplication: three multiply instructions there, no more than the additional table reads.)
+// Measured on B200 against the old form (profiles/r02_variants.log block 14): bit-exact everywhere, and 3-4 % fewer multiply-pipe cycles at
+// an unchanged instruction count in the SASS, but only the cluster kernel of N = 2^15 gains (inverse 216.7 -> 212.9 us, -1.8 %); the
+// tile kernels lose -- N = 1024 +1.6 %, N = 4096 +0.3 %, N = 8192 +8 %, N = 16384 +6.6 % -- because the additional twiddle registers
+// of the first pass spill at their register budgets (72 / 128).  So it is on for N = 2^15 only; -DNFLGPU_FOLD=1 / 0 forces it on for
+// every 64-bit size / off.
+NFLGPU_HD constexpr bool plan_fold(int n, int word_bits) {
+#ifdef NFLGPU_FOLD
+  return NFLGPU_FOLD != 0 && word_bits == 64 && n >= 1;
+#else
+  return word_bits == 64 && n == 15;
+#endif
+}
+// entries per residue of the inverse twiddle table
+NFLGPU_HD constexpr int plan_inv_entries(int n, int word_bits) { return plan_fold(n, word_bits) ? (1 << n) + (1 << (n - 1)) : (1 << n); }
+
 }  // namespace nflgpu
 #endif

@@ -39,7 +39,10 @@ void build_residue_tables(int limb_bits, int word_bits, size_t N, uint64_t p, ui
   pw[0] = ipw[0] = 1;
   for (size_t i = 1; i < N; ++i) { pw[i] = mm(pw[i - 1], psi, p); ipw[i] = mm(ipw[i - 1], ipsi, p); }
 
-  out->fwd_w.assign(N, 0); out->fwd_ws.assign(N, 0); out->inv_w.assign(N, 0); out->inv_ws.assign(N, 0);
+  const bool fold = plan_fold(n, word_bits);  // N^-1 carried by the twiddles (ntt_plan.h plan_fold)
+  const uint64_t scale = raw ? 1 : ninv;      // (core::inv_ntt leaves the scaling to the twist that follows it, core.hpp:539-557,613)
+  out->fwd_w.assign(N, 0); out->fwd_ws.assign(N, 0);
+  out->inv_w.assign((size_t)plan_inv_entries(n, word_bits), 0); out->inv_ws.assign((size_t)plan_inv_entries(n, word_bits), 0);
   const int np = plan_npass(n, word_bits);
   for (int i = 0; i < np && n > 0; ++i) {
     const int r = plan_r(n, word_bits, i), s0 = plan_s0(n, word_bits, i);
@@ -54,15 +57,25 @@ void build_residue_tables(int limb_bits, int word_bits, size_t N, uint64_t p, ui
           size_t ex = raw ? (bitrev(k, n) - ((size_t)1 << (n - 1 - (s0 + q)))) : bitrev(k, n);
           size_t at = off + e_idx * G + g;
           uint64_t w = pw[ex], iw = ipw[ex];
-          if (k == 1 && !raw) iw = mm(iw, ninv, p);  // last inverse stage also scales by N^-1
+          const uint64_t iws = mm(iw, scale, p);
           out->fwd_w[at] = w; out->fwd_ws[at] = shoup_of(w, p, limb_bits);
-          out->inv_w[at] = iw; out->inv_ws[at] = shoup_of(iw, p, limb_bits);
+          if (fold) {
+            // plain, except the stage that pairs position bit 0 (forward stage n-1), whose butterflies all take the scaled twiddle;
+            // the other stages of that pass (the last of the plan) have their scaled copies behind the table, same [e_idx][g] order
+            const uint64_t m = (s0 + q == n - 1) ? iws : iw;
+            out->inv_w[at] = m; out->inv_ws[at] = shoup_of(m, p, limb_bits);
+            if (i == np - 1 && s0 + q != n - 1) {
+              out->inv_w[N + e_idx * G + g] = iws; out->inv_ws[N + e_idx * G + g] = shoup_of(iws, p, limb_bits);
+            }
+          } else {
+            const uint64_t m = (k == 1) ? iws : iw;  // the last inverse stage also scales its difference output by N^-1
+            out->inv_w[at] = m; out->inv_ws[at] = shoup_of(m, p, limb_bits);
+          }
         }
   }
-  // slot N-1: the factor applied to the (U+V) output of the last inverse stage: N^-1, or 1 for the raw transform
-  // (core::inv_ntt leaves the scaling to the twist that follows it, core.hpp:539-557,613)
-  out->inv_w[N - 1] = raw ? 1 : ninv;
-  out->inv_ws[N - 1] = shoup_of(raw ? 1 : ninv, p, limb_bits);
+  // slot N-1: N^-1 (1 for the raw transform) -- applied to the (U+V) output of the last inverse stage, or with folded tables to register 0 of every thread after the first inverse pass
+  out->inv_w[N - 1] = scale;
+  out->inv_ws[N - 1] = shoup_of(scale, p, limb_bits);
 }
 
 }  // namespace nflgpu

@@ -102,8 +102,9 @@ template <int LB, int LOGN> int sim_tile(int inverse, uint64_t p, uint64_t root,
   if (C::SPLIT != 0 || C::NP < 2) return -1;
   ResidueTables t;
   build_residue_tables(LB, C::WB, C::N, p, root, kmax, &t, false);
-  std::vector<TW> tw(C::N);
-  for (int i = 0; i < C::N; ++i) {
+  const int entries = inverse ? C::INV_TW : C::N;  // (the inverse table has a second, N^-1-scaled half when C::FOLD)
+  std::vector<TW> tw(entries);
+  for (int i = 0; i < entries; ++i) {
     tw[i].x = (Word)(inverse ? t.inv_w[i] : t.fwd_w[i]);
     tw[i].y = (Word)(inverse ? t.inv_ws[i] : t.fwd_ws[i]);
   }
@@ -144,8 +145,9 @@ template <int LB, int LOGN> int sim_one(int inverse, uint64_t p, uint64_t root, 
   typedef typename C::TW TW;
   ResidueTables t;
   build_residue_tables(LB, C::WB, C::N, p, root, kmax, &t, false);
-  std::vector<TW> tw(C::N);
-  for (int i = 0; i < C::N; ++i) {
+  const int entries = inverse ? C::INV_TW : C::N;  // (the inverse table has a second, N^-1-scaled half when C::FOLD)
+  std::vector<TW> tw(entries);
+  for (int i = 0; i < entries; ++i) {
     tw[i].x = (Word)(inverse ? t.inv_w[i] : t.fwd_w[i]);
     tw[i].y = (Word)(inverse ? t.inv_ws[i] : t.fwd_ws[i]);
   }

@@ -13,19 +13,22 @@ from oracle_lib import Oracle, random_polys, golden_params, DTYPES
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SIM_SO = os.path.join(ROOT, "tests", "cpp", "libenginesim.so")
 
-_lib = None
+# the same file built with -DNFLGPU_FOLD=1: N^-1 folded into the inverse twiddles of every 64-bit size (ntt_plan.h plan_fold)
+SIM_FOLD_SO = os.path.join(ROOT, "tests", "cpp", "libenginesim_fold.so")
+
+_libs = {}
 
 
-def sim():
-    global _lib
-    if _lib is None:
-        assert os.path.exists(SIM_SO), "run __graft_entry__.build()"
-        _lib = ctypes.CDLL(SIM_SO)
-        _lib.nflsim_ntt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
-                                    ctypes.c_void_p]
-        _lib.nflsim_ntt_tile.argtypes = _lib.nflsim_ntt.argtypes
-        _lib.nflsim_pointwise.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64] + [ctypes.c_void_p] * 5 + [ctypes.c_size_t]
-    return _lib
+def sim(path=SIM_SO):
+    if path not in _libs:
+        assert os.path.exists(path), "run __graft_entry__.build()"
+        lib = ctypes.CDLL(path)
+        lib.nflsim_ntt.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+                                   ctypes.c_void_p]
+        lib.nflsim_ntt_tile.argtypes = lib.nflsim_ntt.argtypes
+        lib.nflsim_pointwise.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_uint64] + [ctypes.c_void_p] * 5 + [ctypes.c_size_t]
+        _libs[path] = lib
+    return _libs[path]
 
 
 PW = {"add": 0, "sub": 1, "mul": 2, "mul_shoup": 3, "compute_shoup": 4, "muladd": 5, "muladd_shoup": 6}
@@ -45,11 +48,11 @@ def run_pw(bits, M, op, a, b=None, c=None, d=None):
     return out
 
 
-def run_sim(bits, N, M, polys, inverse, tile=False):
+def run_sim(bits, N, M, polys, inverse, tile=False, lib=SIM_SO):
     g = golden_params(bits)
     out = np.empty_like(polys)
     n = N.bit_length() - 1
-    fn = sim().nflsim_ntt_tile if tile else sim().nflsim_ntt
+    fn = sim(lib).nflsim_ntt_tile if tile else sim(lib).nflsim_ntt
     for b in range(polys.shape[0]):
         for cm in range(M):
             d = np.ascontiguousarray(polys[b, cm].astype(np.uint64))
@@ -87,6 +90,20 @@ def test_kernel_butterfly_networks_on_the_host_match_the_oracle(bits, N):
     assert np.array_equal(back, a)
     # the inverse on arbitrary canonical input (not only on forward outputs)
     assert np.array_equal(run_sim(bits, N, M, a, inverse=True), o.run("inv", a))
+
+
+@pytest.mark.parametrize("N", [1 << n for n in range(2, 18)])
+def test_inverse_with_folded_scaling_on_the_host(N):
+    """The inverse networks with N^-1 carried by the twiddles of the first inverse pass (one multiplication per thread instead of one
+    per butterfly of the last stage), forced on for every 64-bit size: one-pass, multi-pass and split shapes, flat and through the tile."""
+    bits, M = 64, 2
+    o = Oracle(bits, N, M)
+    a = np.concatenate([random_polys(bits, N, M, 2 if N <= 4096 else 1, 7200 + N), edge_polys(bits, N, M)])
+    want = o.run("inv", a)
+    assert np.array_equal(run_sim(bits, N, M, a, inverse=True, lib=SIM_FOLD_SO), want)
+    if 64 <= N <= 16384:
+        assert np.array_equal(run_sim(bits, N, M, a, inverse=True, tile=True, lib=SIM_FOLD_SO), want)
+    assert np.array_equal(run_sim(bits, N, M, a, inverse=False, lib=SIM_FOLD_SO), o.run("fwd", a))  # (forward: unchanged)
 
 
 TILE_SIZES = ([(64, 1 << n) for n in range(6, 15)] + [(32, 1 << n) for n in range(7, 16)] + [(16, 1 << n) for n in range(7, 10)])

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(THREADS, MINB) ceiling_kernel(const typename N
   typedef typename C::TW TW;
   extern __shared__ __align__(16) unsigned char smem[];
   TW *tws = reinterpret_cast<TW *>(smem);
-  for (int i = threadIdx.x; i < C::N; i += blockDim.x) tws[i] = twg[i];
+  for (int i = threadIdx.x; i < (INV ? C::INV_TW : C::N); i += blockDim.x) tws[i] = twg[i];  // (inverse: the N^-1-scaled half too, NttCfg::FOLD)
   __syncthreads();
   const Word twop = 2 * p, np = opaque_neg(p);
   const TW ninv = tws[C::N - 1];
@@ -42,26 +42,26 @@ template <int LB, int LOGN, int PASS, bool INV, int THREADS, int MINB> void run(
   typedef typename C::Word Word;
   typedef typename C::TW TW;
   const Word p = LB == 64 ? (Word)4611686018326724609ull : (Word)1073479681u;
-  std::vector<TW> h(C::N);
+  std::vector<TW> h(C::INV_TW);
   uint64_t s = 88172645463325252ull;
-  for (int i = 0; i < C::N; ++i) {  // any (w, floor(w * 2^w / p)) pairs will do for timing
+  for (int i = 0; i < C::INV_TW; ++i) {  // any (w, floor(w * 2^w / p)) pairs will do for timing
     s ^= s << 13; s ^= s >> 7; s ^= s << 17;
     const Word w = (Word)(s % p);
     h[i].x = w;
     h[i].y = (Word)((((unsigned __int128)w) << C::WB) / p);
   }
   TW *tw; Word *out;
-  cudaMalloc(&tw, sizeof(TW) * C::N); cudaMalloc(&out, sizeof(Word) * 148 * MINB * THREADS);
-  cudaMemcpy(tw, h.data(), sizeof(TW) * C::N, cudaMemcpyHostToDevice);
+  cudaMalloc(&tw, sizeof(TW) * C::INV_TW); cudaMalloc(&out, sizeof(Word) * 148 * MINB * THREADS);
+  cudaMemcpy(tw, h.data(), sizeof(TW) * C::INV_TW, cudaMemcpyHostToDevice);
   auto k = ceiling_kernel<LB, LOGN, PASS, INV, THREADS, MINB>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TW) * C::N));
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(TW) * C::INV_TW));
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, sizeof(TW) * C::N);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, THREADS, sizeof(TW) * C::INV_TW);
   const int iters = 2000;
-  k<<<148 * MINB, THREADS, sizeof(TW) * C::N>>>(tw, p, out, 10);
+  k<<<148 * MINB, THREADS, sizeof(TW) * C::INV_TW>>>(tw, p, out, 10);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0);
-  k<<<148 * MINB, THREADS, sizeof(TW) * C::N>>>(tw, p, out, iters);
+  k<<<148 * MINB, THREADS, sizeof(TW) * C::INV_TW>>>(tw, p, out, iters);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms, e0, e1);
   constexpr int r = plan_r(C::n, C::WB, PASS);
