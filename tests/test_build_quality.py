@@ -96,3 +96,16 @@ def test_round2_mechanisms_are_in_the_binary():
     r = resources()
     for k in (FWD12_32, INV12_32):
         assert r[k]["reg"] <= 64 and r[k]["stack"] == 0, (k, r[k])
+
+
+CLINV15 = "_ZN6nflgpu22ntt_cluster_inv_kernelILi64ELi15EEEvNS_11ClusterArgsE"
+
+
+def test_folded_scaling_of_the_cluster_inverse_is_in_the_binary():
+    """ntt_plan.h plan_fold: the N = 2^15 cluster inverse carries N^-1 in the twiddles of its first pass and multiplies x[0] once per
+    thread -- 240 butterflies x 6 IMAD.WIDE + one more product -- where the other 64-bit inverse kernels multiply every sum output of
+    the last stage (N = 16384: 224 butterflies + 16 of those = 240 products)."""
+    wide15 = sum(o.startswith("IMAD.WIDE") for o in sass(CLINV15))
+    assert 240 * 6 <= wide15 <= 240 * 6 + 24, wide15
+    wide14 = sum(o.startswith("IMAD.WIDE") for o in sass(INV14))
+    assert wide14 >= (224 + 16) * 6, wide14
