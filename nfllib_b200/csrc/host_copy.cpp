@@ -4,7 +4,7 @@
 // exactly these copies (two per chunk).  So: a small pool of persistent copy threads (no thread creation per chunk), each
 // moving a disjoint slice, and non-temporal stores where the CPU has AVX2 -- the destination of a staging copy is either read
 // next by the DMA engine or far larger than the caches, so write-allocating it only doubles the store traffic.
-// NFLGPU_HOST_COPY_THREADS sets the pool size (default min(8, half the hardware threads); 1 = copy on the calling thread).
+// NFLGPU_HOST_COPY_THREADS sets the pool size (default min(12, three quarters of the hardware threads); 1 = copy on the calling thread).
 #include "host_common.hpp"
 
 #include <condition_variable>
@@ -124,8 +124,10 @@ class CopyPool {
 void staging_copy(void *dst, const void *src, size_t bytes) {
   static const unsigned want = [] {
     const char *e = std::getenv("NFLGPU_HOST_COPY_THREADS");
-    long hw = (long)std::thread::hardware_concurrency() / 2;
-    long v = e ? std::atol(e) : (hw < 2 ? 2 : hw > 8 ? 8 : hw);
+    // three quarters of the hardware threads, at most 12 (measured on the 16-thread B200 host, profiles/r02_variants.log block 16:
+    // 4 / 8 / 12 / 16 threads = 0.66 / 0.85-0.89 / 1.00 / 0.96 M transforms/s for blocking calls on pageable C2 batches)
+    long hw = (long)std::thread::hardware_concurrency() * 3 / 4;
+    long v = e ? std::atol(e) : (hw < 2 ? 2 : hw > 12 ? 12 : hw);
     return (unsigned)(v < 1 ? 1 : v > 16 ? 16 : v);
   }();
   if (bytes < ((size_t)1 << 20) || want == 1) {
